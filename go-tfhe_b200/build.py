@@ -1,0 +1,56 @@
+"""Builds the native libraries in-tree (go-tfhe_b200/lib/):
+  libtfhe_b200.so         CUDA engine + C ABI, nvcc for sm_100a only
+  libtfhe_b200_client.so  host-side client helpers, g++
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(HERE, "lib")
+CSRC = os.path.join(HERE, "csrc")
+ENGINE = os.path.join(LIBDIR, "libtfhe_b200.so")
+CLIENT = os.path.join(LIBDIR, "libtfhe_b200_client.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    eng_src = [os.path.join(CSRC, f) for f in ("tfhe_b200.cu", "blind_rotate.cuh", "lwe_kernels.cuh")] + \
+              [os.path.join(inc, "tfhe_b200.h")]
+    if force or _stale(ENGINE, eng_src):
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-o", ENGINE, os.path.join(CSRC, "tfhe_b200.cu")]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or res.returncode:
+            print(res.stdout + res.stderr)
+        if res.returncode:
+            raise RuntimeError("nvcc failed")
+        with open(os.path.join(LIBDIR, "ptxas_info.txt"), "w") as f:
+            f.write(res.stderr)
+    cl_src = [os.path.join(CSRC, "client.cpp"), os.path.join(inc, "tfhe_b200.h")]
+    if force or _stale(CLIENT, cl_src):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", CLIENT,
+                               os.path.join(CSRC, "client.cpp")])
+    return ENGINE, CLIENT
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose=True))

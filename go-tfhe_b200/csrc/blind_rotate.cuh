@@ -1,0 +1,447 @@
+// blind_rotate.cuh — fused blind-rotation kernel (one thread block per gate) for sm_100a.
+//
+// Replaces, for a whole batch of independent ciphertexts, the reference's
+//   Evaluator.BlindRotateAssign   evaluator/evaluator.go:110-135   (n CMUX steps)
+//   Evaluator.CMuxAssign          evaluator/evaluator.go:85-106
+//   Evaluator.ExternalProductAssign evaluator/evaluator.go:50-81
+//   poly.DecomposePolyAssign      poly/decomposer.go:55-66
+//   Evaluator.ToFourierPolyAssign / ToPolyAssignUnsafe / MulAddFourierPolyAssign
+//                                 poly/fourier_transform.go:18-125,170-347, poly/fourier_ops.go:167-191
+//   poly.PolyMulWithXKInPlace     poly/buffer_methods.go:133-164
+//   trlwe.SampleExtractIndexAssign(k = 0)  trlwe/trlwe_ops.go:10-21  (epilogue)
+//
+// Design: the accumulator TRLWE lives in shared memory for all n steps; each of
+// the T = N/16 threads owns 8 complex points of every transform in registers.  The negacyclic
+// transform is the same factorisation the reference uses (split x^M - c into x^(M/2) -+ sqrt(c),
+// so the fold twist is inside the twiddles and spectra come out in the reference's own order,
+// which lets the bootstrapping key be used as uploaded), but run as radix-8 register passes with
+// FMA butterflies and bank-conflict-free swizzled shared-memory exchanges between passes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfhe {
+
+struct Tw4 { double2 s[4]; };  // twiddles of one radix-8 block: S(m,i), S(2m,2i), S(4m,4i), S(4m,4i+2)
+
+struct BrArgs {
+  const uint32_t* ct_in;    // [count][n+1]  (already linearly combined)
+  const uint32_t* testvec;  // [2][N] default test vector
+  const uint32_t* luts;     // NULL or [nluts][2][N]
+  long long nluts;
+  const double2* bsk;       // [n][2L][2][8][T], pre-scaled by 1/M
+  const double2* tw_tab;    // per-pass twiddle tables for passes >= 1 (4 double2 per block)
+  uint32_t* out;            // out_mode 0: TRLWE [count][2][N]; 1: extracted LWE [count][N+1]
+  int n;
+  uint32_t offset;          // CloudKey.DecompositionOffset
+  int out_mode;
+  Tw4 tw0;                  // pass-0 twiddles (same for every thread; lives in the constant bank)
+};
+
+struct CmuxArgs {
+  const uint32_t* ct0;      // NULL => zero (plain external product)
+  const uint32_t* ct1;      // [count][2][N]
+  const double2* bsk_row;   // [2L][2][8][T]
+  const double2* tw_tab;
+  uint32_t* out;            // [count][2][N]
+  uint32_t offset;
+  Tw4 tw0;
+};
+
+// ---------------------------------------------------------------------------------------------
+// butterflies.  Forward: (u, v) -> (u + w v, u - w v) in 6 FMA (second output as 2u - first).
+// Inverse: (u, v) -> (u + v, (u - v) conj(w)).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bf_fwd(double2& u, double2& v, double wr, double wi) {
+  double tr = fma(v.x, wr, u.x);
+  tr = fma(-v.y, wi, tr);
+  double ti = fma(v.x, wi, u.y);
+  ti = fma(v.y, wr, ti);
+  v.x = fma(2.0, u.x, -tr);
+  v.y = fma(2.0, u.y, -ti);
+  u.x = tr;
+  u.y = ti;
+}
+__device__ __forceinline__ void bf_inv(double2& u, double2& v, double wr, double wi) {
+  double dx = u.x - v.x, dy = u.y - v.y;
+  u.x += v.x;
+  u.y += v.y;
+  v.x = fma(dx, wr, dy * wi);
+  v.y = fma(dy, wr, -(dx * wi));
+}
+
+// Radix-8 block on 8 register-resident points x[0..7] = block elements at stride s.
+// NST = 3: stages A,B,C; 2: B,C; 1: C.  Block 2i+1 uses -i * S(2m,2i) (= (wi, -wr)), etc.
+template <int NST>
+__device__ __forceinline__ void radix8_fwd(double2 (&x)[8], const double2& s0, const double2& s1, const double2& s2,
+                                           const double2& s3) {
+  if constexpr (NST >= 3) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) bf_fwd(x[k], x[k + 4], s0.x, s0.y);
+  }
+  if constexpr (NST >= 2) {
+    bf_fwd(x[0], x[2], s1.x, s1.y);
+    bf_fwd(x[1], x[3], s1.x, s1.y);
+    bf_fwd(x[4], x[6], s1.y, -s1.x);
+    bf_fwd(x[5], x[7], s1.y, -s1.x);
+  }
+  bf_fwd(x[0], x[1], s2.x, s2.y);
+  bf_fwd(x[2], x[3], s2.y, -s2.x);
+  bf_fwd(x[4], x[5], s3.x, s3.y);
+  bf_fwd(x[6], x[7], s3.y, -s3.x);
+}
+template <int NST>
+__device__ __forceinline__ void radix8_inv(double2 (&x)[8], const double2& s0, const double2& s1, const double2& s2,
+                                           const double2& s3) {
+  bf_inv(x[0], x[1], s2.x, s2.y);
+  bf_inv(x[2], x[3], s2.y, -s2.x);
+  bf_inv(x[4], x[5], s3.x, s3.y);
+  bf_inv(x[6], x[7], s3.y, -s3.x);
+  if constexpr (NST >= 2) {
+    bf_inv(x[0], x[2], s1.x, s1.y);
+    bf_inv(x[1], x[3], s1.x, s1.y);
+    bf_inv(x[4], x[6], s1.y, -s1.x);
+    bf_inv(x[5], x[7], s1.y, -s1.x);
+  }
+  if constexpr (NST >= 3) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) bf_inv(x[k], x[k + 4], s0.x, s0.y);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pass geometry for an M = 2^LOGM point transform with T = M/8 threads.
+// Full pass k (0-based) works on elements at stride s_k = M >> 3(k+1); if LOGM is not a multiple
+// of 3 a final partial pass (stride 1, 8 contiguous points) runs the last LOGM % 3 stages.
+// ---------------------------------------------------------------------------------------------
+template <int LOGM>
+struct Geo {
+  static constexpr int M = 1 << LOGM;
+  static constexpr int T = M / 8;
+  static constexpr int NFULL = LOGM / 3;
+  static constexpr int REM = LOGM % 3;
+  static constexpr int NPASS = NFULL + (REM ? 1 : 0);
+  __host__ __device__ static constexpr int stride(int k) { return k < NFULL ? (M >> (3 * (k + 1))) : 1; }
+  __host__ __device__ static constexpr int nstages(int k) { return k < NFULL ? 3 : REM; }
+  // number of blocks entering pass k (twiddle table length), and table offset (in Tw4 units) for k >= 1
+  __host__ __device__ static constexpr int blocks(int k) { return k < NFULL ? (1 << (3 * k)) : T; }
+  __host__ __device__ static constexpr int tab_off(int k) {
+    int o = 0;
+    for (int q = 1; q < k; q++) o += blocks(q);
+    return o;
+  }
+  __host__ __device__ static constexpr int tab_len() { return tab_off(NPASS); }
+  // first element position of thread tau in pass k; element a sits at base + stride(k) * a
+  __device__ __forceinline__ static int base(int k, int tau) {
+    const int s = stride(k);
+    return (tau / s) * (8 * s) + (tau % s);
+  }
+  __device__ __forceinline__ static int block_of(int k, int tau) { return tau / stride(k); }
+};
+
+// 16-byte-slot swizzle: conflict-free for every pass stride used above.
+__device__ __forceinline__ int swz(int p) { return p ^ ((p >> 3) & 7); }
+
+template <int LOGM>
+struct Fft {
+  using G = Geo<LOGM>;
+  // Per-thread persistent state: twiddles of the last pass (unique per thread) and the ping-pong
+  // parity of the exchange buffers.
+  double2 tl0, tl1, tl2, tl3;
+  int parity;
+  double2* ex;            // [2][M] exchange buffers in shared memory
+  const Tw4* tab;         // twiddle tables for passes >= 1
+  int tau;
+
+  __device__ __forceinline__ void init(double2* ex_, const double2* tw_tab, int tau_) {
+    ex = ex_;
+    tab = reinterpret_cast<const Tw4*>(tw_tab);
+    tau = tau_;
+    parity = 0;
+    const Tw4* e = tab + G::tab_off(G::NPASS - 1) + G::block_of(G::NPASS - 1, tau);
+    tl0 = e->s[0]; tl1 = e->s[1]; tl2 = e->s[2]; tl3 = e->s[3];
+  }
+
+  template <int KW, int KR>
+  __device__ __forceinline__ void exchange(double2 (&x)[8]) {
+    double2* buf = ex + (parity ? G::M : 0);
+    parity ^= 1;
+    const int wb = G::base(KW, tau), rb = G::base(KR, tau);
+#pragma unroll
+    for (int a = 0; a < 8; a++) buf[swz(wb + G::stride(KW) * a)] = x[a];
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 8; a++) x[a] = buf[swz(rb + G::stride(KR) * a)];
+  }
+
+  template <int K>
+  __device__ __forceinline__ void fwd_pass(double2 (&x)[8], const Tw4& tw0) {
+    if constexpr (K == 0) {
+      radix8_fwd<3>(x, tw0.s[0], tw0.s[1], tw0.s[2], tw0.s[3]);
+    } else if constexpr (K == G::NPASS - 1) {
+      radix8_fwd<G::nstages(K)>(x, tl0, tl1, tl2, tl3);
+    } else {
+      const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
+      double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
+      radix8_fwd<3>(x, s0, s1, s2, s3);
+    }
+  }
+  template <int K>
+  __device__ __forceinline__ void inv_pass(double2 (&x)[8], const Tw4& tw0) {
+    if constexpr (K == 0) {
+      radix8_inv<3>(x, tw0.s[0], tw0.s[1], tw0.s[2], tw0.s[3]);
+    } else if constexpr (K == G::NPASS - 1) {
+      radix8_inv<G::nstages(K)>(x, tl0, tl1, tl2, tl3);
+    } else {
+      const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
+      double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
+      radix8_inv<3>(x, s0, s1, s2, s3);
+    }
+  }
+
+  // in: x[a] = z[tau + T a] (folded coefficients); out: x[e] = spectrum at position 8 tau + e
+  __device__ __forceinline__ void forward(double2 (&x)[8], const Tw4& tw0) {
+    fwd_pass<0>(x, tw0);
+    if constexpr (G::NPASS > 1) { exchange<0, 1>(x); fwd_pass<1>(x, tw0); }
+    if constexpr (G::NPASS > 2) { exchange<1, 2>(x); fwd_pass<2>(x, tw0); }
+    if constexpr (G::NPASS > 3) { exchange<2, 3>(x); fwd_pass<3>(x, tw0); }
+  }
+  // exact inverse of forward() up to the factor M (folded into the bootstrapping key)
+  __device__ __forceinline__ void inverse(double2 (&x)[8], const Tw4& tw0) {
+    if constexpr (G::NPASS > 3) { inv_pass<3>(x, tw0); exchange<3, 2>(x); }
+    if constexpr (G::NPASS > 2) { inv_pass<2>(x, tw0); exchange<2, 1>(x); }
+    if constexpr (G::NPASS > 1) { inv_pass<1>(x, tw0); exchange<1, 0>(x); }
+    inv_pass<0>(x, tw0);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------------------------
+// exact int -> double for 0 <= field < 2^32 minus a constant bias, without I2F:
+// bits(2^52 + field) then one DADD.
+__device__ __forceinline__ double field_to_double(uint32_t field, double bias) {
+  return __hiloint2double(0x43300000, (int)field) - bias;
+}
+
+// Spectrum-domain result -> torus word.  poly/fourier_transform.go:88-125: round(x - 2^32 round(x / 2^32))
+// then uint32(int64(.)).  SMALL: |y| < 2^51 guaranteed by the parameter set, so one magic-number add
+// yields round-to-nearest(y) mod 2^32 (ties cannot occur where the result is exact).
+template <bool SMALL>
+__device__ __forceinline__ uint32_t to_torus(double y) {
+  if (!SMALL) {
+    double q = rint(y * (1.0 / 4294967296.0));
+    y = fma(-4294967296.0, q, y);
+  }
+  return (uint32_t)__double2loint(y + 6755399441055744.0);
+}
+
+// value of (X^k * P)[j] given idx = (j - k) mod 2N: P[idx] or ~P[idx - N]  (buffer_methods.go:133-164;
+// the wrap-around "negation" is 0xFFFFFFFF - a, not -a)
+template <int N>
+__device__ __forceinline__ uint32_t rot_read(const uint32_t* P, int idx) {
+  uint32_t v = P[idx & (N - 1)];
+  return (idx & N) ? ~v : v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One CMUX step on the shared-memory accumulator: acc += BK (x) (X^at * acc - acc).
+// ---------------------------------------------------------------------------------------------
+template <int LOGN, int L, int BGBIT, bool SMALL>
+__device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1>& fft, const double2* __restrict__ bk,
+                                                 int at, uint32_t offset, const Tw4& tw0) {
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  const int tau = fft.tau;
+  double2 accA[8], accB[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
+
+#pragma unroll
+  for (int poly = 0; poly < 2; poly++) {
+    const uint32_t* P = acc + poly * N;
+    uint32_t dre[8], dim[8];
+    const int ib = (tau - at) & (2 * N - 1);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      dre[a] = rot_read<N>(P, ib + T * a) - P[j] + offset;
+      dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + offset;
+    }
+#pragma unroll
+    for (int lvl = 0; lvl < L; lvl++) {
+      double2 x[8];
+      constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+      const int sh = 32 - (lvl + 1) * BGBIT;
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
+        x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+      }
+      fft.forward(x, tw0);
+      const double2* __restrict__ rowA = bk + ((poly * L + lvl) * 2 + 0) * M + tau;
+      const double2* __restrict__ rowB = rowA + M;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const double2 ka = __ldg(rowA + e * T);
+        const double2 kb = __ldg(rowB + e * T);
+        accA[e].x = fma(x[e].x, ka.x, accA[e].x);
+        accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
+        accA[e].y = fma(x[e].x, ka.y, accA[e].y);
+        accA[e].y = fma(x[e].y, ka.x, accA[e].y);
+        accB[e].x = fma(x[e].x, kb.x, accB[e].x);
+        accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
+        accB[e].y = fma(x[e].x, kb.y, accB[e].y);
+        accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+      }
+    }
+  }
+  fft.inverse(accA, tw0);
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int j = tau + T * a;
+    acc[j] += to_torus<SMALL>(accA[a].x);
+    acc[j + M] += to_torus<SMALL>(accA[a].y);
+  }
+  fft.inverse(accB, tw0);
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int j = tau + T * a;
+    acc[N + j] += to_torus<SMALL>(accB[a].x);
+    acc[N + j + M] += to_torus<SMALL>(accB[a].y);
+  }
+}
+
+template <int LOGN>
+constexpr size_t br_smem_bytes(int n) {
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * (1 << (LOGN - 1)) * 16 /*exchange*/ +
+         (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel: grid = count gates, block = T = N/16 threads.
+// ---------------------------------------------------------------------------------------------
+template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
+__global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_kernel(const BrArgs A) {
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][M]
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 32 * M);
+  const int tau = threadIdx.x;
+  const long long g = blockIdx.x;
+  const int n = A.n;
+  const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+
+  // mod switch (evaluator.go:116,122): a~_i = ((a_i + 2^(30-NBIT)) mod 2^32) >> (31-NBIT)
+  for (int i = tau; i < n; i += T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
+  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
+  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
+  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+  {  // acc = X^btil * testvec
+    for (int j = tau; j < N; j += T) {
+      const int idx = (j - btil) & (2 * N - 1);
+      const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
+      acc[j] = (idx & N) ? ~va : va;
+      acc[N + j] = (idx & N) ? ~vb : vb;
+    }
+  }
+  Fft<LOGN - 1> fft;
+  fft.init(ex, A.tw_tab, tau);
+  __syncthreads();
+
+  const size_t row_stride = (size_t)2 * L * 2 * M;
+  for (int i = 0; i < n; i++) {
+    const int at = abar[i];
+    if (at == 0) continue;  // X^0: ct1 - ct0 = 0, digits are all zero, the step is an exact no-op
+    cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, A.bsk + row_stride * i, at, A.offset, A.tw0);
+    __syncthreads();
+  }
+
+  if (A.out_mode == 0) {
+    uint32_t* o = A.out + g * (2 * N);
+    for (int j = tau; j < 2 * N; j += T) o[j] = acc[j];
+  } else {  // sample extract at 0 (trlwe_ops.go:10-21): out[0] = A[0], out[i] = ~A[N-i], out[N] = B[0]
+    uint32_t* o = A.out + g * (N + 1);
+    for (int j = tau; j < N; j += T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
+    if (tau == 0) o[N] = acc[N];
+  }
+}
+
+// Single CMUX / external product on global-memory TRLWEs (parity-test granularity; rows a9, a14).
+template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
+__global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const CmuxArgs A) {
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);       // holds ct0, becomes the result
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);
+  uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 32 * M);  // [2][N]
+  const int tau = threadIdx.x;
+  const long long g = blockIdx.x;
+  for (int j = tau; j < 2 * N; j += T) {
+    acc[j] = A.ct0 ? A.ct0[g * 2 * N + j] : 0u;
+    c1[j] = A.ct1[g * 2 * N + j];
+  }
+  Fft<LOGN - 1> fft;
+  fft.init(ex, A.tw_tab, tau);
+  __syncthreads();
+  // Same data path as cmux_rotate_step but the second operand comes from c1 instead of a rotation.
+  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  double2 accA[8], accB[8];
+#pragma unroll
+  for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
+#pragma unroll
+  for (int poly = 0; poly < 2; poly++) {
+    uint32_t dre[8], dim[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = poly * N + tau + T * a;
+      dre[a] = c1[j] - acc[j] + A.offset;
+      dim[a] = c1[j + M] - acc[j + M] + A.offset;
+    }
+#pragma unroll
+    for (int lvl = 0; lvl < L; lvl++) {
+      double2 x[8];
+      constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+      const int sh = 32 - (lvl + 1) * BGBIT;
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
+        x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+      }
+      fft.forward(x, A.tw0);
+      const double2* __restrict__ rowA = A.bsk_row + ((poly * L + lvl) * 2 + 0) * M + tau;
+      const double2* __restrict__ rowB = rowA + M;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const double2 ka = __ldg(rowA + e * T);
+        const double2 kb = __ldg(rowB + e * T);
+        accA[e].x = fma(x[e].x, ka.x, accA[e].x);
+        accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
+        accA[e].y = fma(x[e].x, ka.y, accA[e].y);
+        accA[e].y = fma(x[e].y, ka.x, accA[e].y);
+        accB[e].x = fma(x[e].x, kb.x, accB[e].x);
+        accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
+        accB[e].y = fma(x[e].x, kb.y, accB[e].y);
+        accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+      }
+    }
+  }
+  fft.inverse(accA, A.tw0);
+  uint32_t* o = A.out + g * 2 * N;
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int j = tau + T * a;
+    o[j] = acc[j] + to_torus<SMALL>(accA[a].x);
+    o[j + M] = acc[j + M] + to_torus<SMALL>(accA[a].y);
+  }
+  fft.inverse(accB, A.tw0);
+#pragma unroll
+  for (int a = 0; a < 8; a++) {
+    const int j = tau + T * a;
+    o[N + j] = acc[N + j] + to_torus<SMALL>(accB[a].x);
+    o[N + j + M] = acc[N + j + M] + to_torus<SMALL>(accB[a].y);
+  }
+}
+
+}  // namespace tfhe

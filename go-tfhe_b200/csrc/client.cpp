@@ -1,0 +1,233 @@
+// client.cpp — host-side client operations (key generation, encryption, decryption, LUT
+// construction).  In a real integration these stay in the reference's own Go packages
+// (key/, tlwe/, cloudkey/, lut/) and only the flattened results cross the C ABI; this
+// library is the stand-in used where no Go toolchain exists (this image), so that bench.py
+// and the examples can produce valid keys and ciphertexts WITHOUT touching oracle/.
+// It is an independent implementation: integer-exact ring products (the secret keys are
+// binary, so a*s is a signed sum of rotations), its own RNG, its own transform code.
+//
+// Produces exactly the structures the reference's CloudKey holds (cloudkey/cloudkey.go:16-21),
+// flattened as documented in include/tfhe_b200.h.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/tfhe_b200.h"
+
+namespace {
+
+typedef uint32_t Torus;
+
+// counter-based generator: every (seed, stream, index) triple gives an independent 64-bit word,
+// so results do not depend on the number of worker threads.
+struct Stream {
+  uint64_t key, ctr = 0;
+  Stream(uint64_t seed, uint64_t stream) : key(mix(seed ^ mix(stream + 0x632BE59BD9B4E019ull))) {}
+  static uint64_t mix(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+  }
+  uint64_t u64() { return mix(key + 0xD1342543DE82EF95ull * (++ctr)); }
+  uint32_t u32() { return (uint32_t)(u64() >> 32); }
+  double unit() { return ((u64() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+  double gauss() {  // Box-Muller, one value per call
+    const double u = unit(), v = unit();
+    return std::sqrt(-2.0 * std::log(u)) * std::cos(6.283185307179586476925286766559 * v);
+  }
+};
+
+// real number -> torus, utils.F64ToTorus semantics (utils/utils.go:11-14): frac(d) * 2^32, truncated
+Torus to_torus(double d) {
+  double f = std::fmod(d, 1.0) * 4294967296.0;
+  return (Torus)(uint64_t)(int64_t)f;
+}
+Torus noisy(double mu, double sigma, Stream& rng) { return to_torus(mu) + to_torus(rng.gauss() * sigma); }
+
+void lwe_encrypt(const tfhe_params& P, double mu, double sigma, const Torus* s0, Stream& rng, Torus* out) {
+  Torus dot = 0;
+  for (int i = 0; i < P.n; i++) {
+    out[i] = rng.u32();
+    dot += out[i] * s0[i];
+  }
+  out[P.n] = dot + noisy(mu, sigma, rng);
+}
+
+// (a * s) in Z[X]/(X^N+1) for binary s, exact mod 2^32
+void ring_mul_binary(const Torus* a, const Torus* s, int N, Torus* out) {
+  std::memset(out, 0, sizeof(Torus) * N);
+  for (int j = 0; j < N; j++) {
+    if (!s[j]) continue;
+    for (int i = 0; i < N - j; i++) out[i + j] += a[i];
+    for (int i = N - j; i < N; i++) out[i + j - N] -= a[i];
+  }
+}
+
+// Transform of the reference's FourierPoly: evaluate the folded polynomial z_j = p_j + i p_{j+N/2}
+// at the roots of x^(N/2) = i by repeatedly splitting x^m - c into x^(m/2) -+ sqrt(c).  The order of
+// the outputs and the 4-real/4-imaginary packing are those of poly/fourier_transform.go.
+struct Spectrum {
+  int N, M;
+  std::vector<double> wr, wi;  // sqrt table, stage-major: entry (m - 1 + i) for block i of stage m
+  explicit Spectrum(int N_) : N(N_), M(N_ / 2), wr(M), wi(M) {
+    int bits = 0;
+    while ((1 << bits) < M / 2) bits++;
+    const long double pi = 3.14159265358979323846264338327950288L;
+    for (int m = 1; m <= M / 2; m <<= 1)
+      for (int i = 0; i < m; i++) {
+        int r = 0;
+        for (int b = 0; b < bits; b++)
+          if (i & (1 << b)) r |= 1 << (bits - 1 - b);
+        long double ang = -2.0L * pi * r / M + pi / (4.0L * m);
+        wr[m - 1 + i] = (double)cosl(ang);
+        wi[m - 1 + i] = (double)sinl(ang);
+      }
+  }
+  void forward(const Torus* p, double* out) const {
+    std::vector<double> re(M), im(M);
+    for (int j = 0; j < M; j++) { re[j] = (double)(int32_t)p[j]; im[j] = (double)(int32_t)p[j + M]; }
+    for (int m = 1, half = M / 2; m <= M / 2; m <<= 1, half >>= 1)
+      for (int i = 0; i < m; i++) {
+        const double cr = wr[m - 1 + i], ci = wi[m - 1 + i];
+        const int lo = 2 * i * half;
+        for (int j = lo; j < lo + half; j++) {
+          const double tr = re[j + half] * cr - im[j + half] * ci, ti = re[j + half] * ci + im[j + half] * cr;
+          re[j + half] = re[j] - tr; im[j + half] = im[j] - ti;
+          re[j] += tr; im[j] += ti;
+        }
+      }
+    for (int k = 0; k < M; k++) { out[(k >> 2) * 8 + (k & 3)] = re[k]; out[(k >> 2) * 8 + 4 + (k & 3)] = im[k]; }
+  }
+};
+
+template <class F> void run_parallel(int count, int threads, F f) {
+  if (threads < 1) threads = (int)std::thread::hardware_concurrency();
+  if (threads < 1) threads = 1;
+  if (threads > count) threads = count > 0 ? count : 1;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; t++)
+    pool.emplace_back([=]() { for (int i = t; i < count; i += threads) f(i); });
+  for (auto& th : pool) th.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+// key.NewSecretKey (key/key.go:16-45): uniform binary keys of length n and N.
+void tfhe_client_secret_key(const tfhe_params* P, uint64_t seed, uint32_t* key_lv0, uint32_t* key_lv1) {
+  Stream a(seed, 1), b(seed, 2);
+  for (int i = 0; i < P->n; i++) key_lv0[i] = (uint32_t)(a.u64() >> 63);
+  for (int i = 0; i < P->N; i++) key_lv1[i] = (uint32_t)(b.u64() >> 63);
+}
+
+// tlwe.EncryptBool (tlwe/tlwe.go:54-62): mu = +-1/8.  count ciphertexts, ciphertext g uses stream (seed, g).
+void tfhe_client_encrypt_bool(const tfhe_params* P, double alpha, const uint32_t* key_lv0, uint64_t seed, int64_t count,
+                              const uint8_t* bits, uint32_t* out) {
+  for (int64_t g = 0; g < count; g++) {
+    Stream rng(seed, 0x10000000ull + (uint64_t)g);
+    lwe_encrypt(*P, bits[g] ? 0.125 : -0.125, alpha, key_lv0, rng, out + (size_t)g * (P->n + 1));
+  }
+}
+// tlwe.DecryptBool (tlwe/tlwe.go:65-74)
+void tfhe_client_decrypt_bool(const tfhe_params* P, const uint32_t* key_lv0, int64_t count, const uint32_t* ct,
+                              uint8_t* bits) {
+  for (int64_t g = 0; g < count; g++) {
+    const Torus* c = ct + (size_t)g * (P->n + 1);
+    Torus dot = 0;
+    for (int i = 0; i < P->n; i++) dot += c[i] * key_lv0[i];
+    bits[g] = (int32_t)(c[P->n] - dot) >= 0;
+  }
+}
+// tlwe.EncryptLWEMessage (tlwe/programmable_encrypt.go:12-27): mu = m / (2 * modulus)
+void tfhe_client_encrypt_message(const tfhe_params* P, double alpha, const uint32_t* key_lv0, uint64_t seed,
+                                 int64_t count, const int32_t* msgs, int32_t modulus, uint32_t* out) {
+  for (int64_t g = 0; g < count; g++) {
+    Stream rng(seed, 0x20000000ull + (uint64_t)g);
+    int m = msgs[g] % modulus;
+    if (m < 0) m += modulus;
+    const double mu = (double)m * (2147483648.0 / (double)modulus) / 4294967296.0;
+    lwe_encrypt(*P, mu, alpha, key_lv0, rng, out + (size_t)g * (P->n + 1));
+  }
+}
+// tlwe.DecryptLWEMessage (tlwe/programmable_encrypt.go:33-54)
+void tfhe_client_decrypt_message(const tfhe_params* P, const uint32_t* key_lv0, int64_t count, const uint32_t* ct,
+                                 int32_t modulus, int32_t* msgs) {
+  const Torus scale = (Torus)2147483648u / (Torus)modulus;
+  for (int64_t g = 0; g < count; g++) {
+    const Torus* c = ct + (size_t)g * (P->n + 1);
+    Torus dot = 0;
+    for (int i = 0; i < P->n; i++) dot += c[i] * key_lv0[i];
+    const Torus phase = c[P->n] - dot;
+    msgs[g] = (int32_t)(((Torus)(phase + scale / 2) / scale) % (Torus)modulus);
+  }
+}
+
+// lut.Generator.GenLookUpTable (lut/generator.go:49-100) for fvals[x] = f(x), x in [0, modulus):
+// box x covers table slots [round(xN/mod), round((x+1)N/mod)), the table is rotated left by half a
+// box and the wrapped tail is negated; output is a TRLWE (A = 0, B = table).
+void tfhe_client_gen_lut(const tfhe_params* P, int32_t modulus, const int32_t* fvals, uint32_t* lut_out) {
+  const int N = P->N;
+  std::vector<Torus> box(N, 0);
+  for (int x = 0; x < modulus; x++) {
+    const long lo = ((long)x * N + modulus / 2) / modulus, hi = ((long)(x + 1) * N + modulus / 2) / modulus;
+    int y = fvals[x] % modulus;
+    if (y < 0) y += modulus;
+    const Torus enc = to_torus((double)y * (1.0 / (double)(2 * modulus)));
+    for (long k = lo; k < hi; k++) box[k] = enc;
+  }
+  const long half = ((long)N + modulus) / (2L * modulus);  // round(N / (2 mod))
+  for (int i = 0; i < N; i++) {
+    Torus v = box[(i + half) % N];
+    lut_out[N + i] = (i >= N - half) ? (Torus)0 - v : v;
+    lut_out[i] = 0;
+  }
+}
+
+// cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-31,60-145).  alpha_lv0 = KSKAlpha, alpha_lv1 = BSKAlpha.
+// ksk / bsk_fft may be NULL to skip that part.  threads <= 0 => all hardware threads.
+void tfhe_client_cloud_key(const tfhe_params* Pp, double alpha_lv0, double alpha_lv1, const uint32_t* key_lv0,
+                           const uint32_t* key_lv1, uint64_t seed, int threads, uint32_t* decomposition_offset,
+                           uint32_t* testvec, uint32_t* ksk, double* bsk_fft) {
+  const tfhe_params P = *Pp;
+  Torus off = 0;
+  for (int l = 0; l < P.L; l++) off += (Torus)(1u << (P.bgbit - 1)) << (32 - (l + 1) * P.bgbit);
+  *decomposition_offset = off;
+  for (int i = 0; i < P.N; i++) { testvec[i] = 0; testvec[P.N + i] = 0x20000000u; }
+  const int base = 1 << P.basebit;
+  if (ksk)
+    run_parallel(P.N, threads, [&](int i) {
+      for (int j = 0; j < P.iks_t; j++)
+        for (int k = 0; k < base; k++) {
+          Torus* row = ksk + ((size_t)(i * P.iks_t + j) * base + k) * (P.n + 1);
+          if (k == 0) { std::memset(row, 0, sizeof(Torus) * (P.n + 1)); continue; }
+          Stream rng(seed, 0x40000000ull + ((uint64_t)(i * P.iks_t + j) * base + k));
+          const double mu = (double)k * (double)key_lv1[i] / (double)(1ull << ((j + 1) * P.basebit));
+          lwe_encrypt(P, mu, alpha_lv0, key_lv0, rng, row);
+        }
+    });
+  if (bsk_fft) {
+    const Spectrum spec(P.N);
+    run_parallel(P.n, threads, [&](int i) {
+      const int N = P.N;
+      std::vector<Torus> A(N), B(N), as(N);
+      for (int r = 0; r < 2 * P.L; r++) {  // TRGSW row r: TRLWE encryption of zero plus the gadget term
+        Stream rng(seed, 0x80000000ull + (uint64_t)i * 64 + r);
+        for (int k = 0; k < N; k++) A[k] = rng.u32();
+        ring_mul_binary(A.data(), key_lv1, N, as.data());
+        for (int k = 0; k < N; k++) B[k] = as[k] + noisy(0.0, alpha_lv1, rng);
+        const int lvl = r % P.L;
+        const Torus g = key_lv0[i] * ((Torus)1u << (32 - (lvl + 1) * P.bgbit));  // s_i / Bg^(lvl+1)
+        if (r < P.L) A[0] += g; else B[0] += g;
+        double* dst = bsk_fft + (((size_t)i * 2 * P.L + r) * 2) * N;
+        spec.forward(A.data(), dst);
+        spec.forward(B.data(), dst + N);
+      }
+    });
+  }
+}
+
+}  // extern "C"

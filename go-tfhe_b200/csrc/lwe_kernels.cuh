@@ -1,0 +1,180 @@
+// lwe_kernels.cuh — the integer (u32) kernels either side of the blind rotation:
+//   gate prologues      evaluator/gates_helper.go:10-63, gates/gates.go:52-130
+//   identity key switch trgsw/keyswitch.go:10-37 (= trgsw/trgsw.go:285-311)
+//   sample extract      trlwe/trlwe_ops.go:10-21
+//   key repacking       (layout only; no reference equivalent)
+// All arithmetic is mod 2^32 and bit-exact with the reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tfhe {
+
+// c = sa*a + sb*b + (0,...,0,bias) for one gate per block row.  (sa, sb, bias) per opcode:
+//   NAND (-1,-1,+1/8)  AND (1,1,-1/8)   OR (1,1,+1/8)    XOR (1,2,+1/4)   XNOR (1,-2,+1/4)
+//   NOR (-1,-1,-1/8)   ANDNY (-1,1,-1/8) ANDYN (1,-1,-1/8) ORNY (-1,1,+1/8) ORYN (1,-1,+1/8)
+// with 1/8 = 0x20000000, 1/4 = 0x40000000, -1/8 = 0xE0000000 (utils/utils_test.go:15-19).
+__device__ __forceinline__ void gate_coeffs(int op, uint32_t& sa, uint32_t& sb, uint32_t& bias) {
+  const uint32_t P1 = 1u, M1 = 0xFFFFFFFFu, E8 = 0x20000000u, N8 = 0xE0000000u, Q4 = 0x40000000u;
+  switch (op) {
+    case 0: sa = M1; sb = M1; bias = E8; break;               // NAND
+    case 1: sa = P1; sb = P1; bias = N8; break;               // AND
+    case 2: sa = P1; sb = P1; bias = E8; break;               // OR
+    case 3: sa = P1; sb = 2u; bias = Q4; break;               // XOR
+    case 4: sa = P1; sb = 0xFFFFFFFEu; bias = Q4; break;      // XNOR
+    case 5: sa = M1; sb = M1; bias = N8; break;               // NOR
+    case 6: sa = M1; sb = P1; bias = N8; break;               // ANDNY
+    case 7: sa = P1; sb = M1; bias = N8; break;               // ANDYN
+    case 8: sa = M1; sb = P1; bias = E8; break;               // ORNY
+    case 9: sa = P1; sb = M1; bias = E8; break;               // ORYN
+    case 11: sa = M1; sb = 0u; bias = 0u; break;              // NOT  (0 - a, gates.go:117-119)
+    default: sa = P1; sb = 0u; bias = 0u; break;              // COPY (gates.go:122-126)
+  }
+}
+
+// One job = one prepared ciphertext.  job j reads a_idx[j], b_idx[j] rows (indices into the a / b
+// batches) so that MUX can be expanded into its three bootstraps without copying inputs.
+struct PrepJob {
+  const uint32_t* a;
+  const uint32_t* b;
+  uint32_t* out;
+  int op;
+};
+
+// grid.x = count, block = 256.  ops: [nops] with nops in {1,count}.  For MUX gates (op 10) the
+// first-level jobs are AND(a,b) -> out0[g] and ANDNY(a,c) -> out1[g]  (AND(NOT a, c) == ANDNY(a,c)
+// word for word: (0 - a) + c - 1/8).  Non-MUX gates write their prepared ciphertext to out0[g] and
+// leave out1[g] untouched.  NOT / COPY write their final result to out0 as well (no bootstrap).
+__global__ void gate_prepare_kernel(long long count, const uint8_t* __restrict__ ops, long long nops,
+                                    const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                    const uint32_t* __restrict__ c, uint32_t* __restrict__ out0,
+                                    uint32_t* __restrict__ out1, int n) {
+  const long long g = blockIdx.x;
+  const int op = ops[nops == 1 ? 0 : g];
+  const size_t row = (size_t)g * (n + 1);
+  uint32_t sa, sb, bias;
+  if (op == 10) {
+    gate_coeffs(1, sa, sb, bias);
+    for (int i = threadIdx.x; i <= n; i += blockDim.x)
+      out0[row + i] = sa * a[row + i] + sb * b[row + i] + (i == n ? bias : 0u);
+    gate_coeffs(6, sa, sb, bias);
+    for (int i = threadIdx.x; i <= n; i += blockDim.x)
+      out1[row + i] = sa * a[row + i] + sb * c[row + i] + (i == n ? bias : 0u);
+  } else {
+    gate_coeffs(op, sa, sb, bias);
+    const bool unary = (op >= 11);
+    for (int i = threadIdx.x; i <= n; i += blockDim.x)
+      out0[row + i] = sa * a[row + i] + (unary ? 0u : sb * b[row + i]) + (i == n ? bias : 0u);
+  }
+}
+
+// Second level of MUX: out = OR(x, y) prologue = x + y + 1/8, for gates whose op is MUX.
+__global__ void mux_or_prepare_kernel(long long count, const uint8_t* __restrict__ ops, long long nops,
+                                      const uint32_t* __restrict__ x, const uint32_t* __restrict__ y,
+                                      uint32_t* __restrict__ out, int n) {
+  const long long g = blockIdx.x;
+  const size_t row = (size_t)g * (n + 1);
+  for (int i = threadIdx.x; i <= n; i += blockDim.x)
+    out[row + i] = x[row + i] + y[row + i] + (i == n ? 0x20000000u : 0u);
+}
+
+// gather / scatter of ciphertext rows by index list (used to compact MUX jobs)
+__global__ void gather_rows_kernel(const uint32_t* __restrict__ src, const int* __restrict__ idx,
+                                   uint32_t* __restrict__ dst, int words) {
+  const size_t s = (size_t)idx[blockIdx.x] * words, d = (size_t)blockIdx.x * words;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[d + i] = src[s + i];
+}
+__global__ void scatter_rows_kernel(const uint32_t* __restrict__ src, const int* __restrict__ idx,
+                                    uint32_t* __restrict__ dst, int words) {
+  const size_t d = (size_t)idx[blockIdx.x] * words, s = (size_t)blockIdx.x * words;
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[d + i] = src[s + i];
+}
+
+// trlwe/trlwe_ops.go:10-21 with k = 0
+__global__ void sample_extract_kernel(const uint32_t* __restrict__ trlwe, uint32_t* __restrict__ out, int N) {
+  const long long g = blockIdx.x;
+  const uint32_t* A = trlwe + (size_t)g * 2 * N;
+  uint32_t* o = out + (size_t)g * (N + 1);
+  for (int j = threadIdx.x; j < N; j += blockDim.x) o[j] = (j == 0) ? A[0] : ~A[N - j];
+  if (threadIdx.x == 0) o[N] = A[N];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Identity key switch, one block per ciphertext (v1: gathers its own rows; the rows of all
+// co-resident blocks come out of L2).
+//   out = (0,...,0,b) - sum_{i<N, j<t, k_ij != 0} KSK[i][j][k_ij],  k_ij = digit j of a_i + 2^(31 - basebit*t)
+// ksk rows are padded to `stride` words (multiple of 4) for 16-byte loads.  Row order is the
+// reference's: (base*t*i + base*j + k).  Subtractions commute mod 2^32, so any order is bit-exact.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) key_switch_kernel(const uint32_t* __restrict__ lwe_in,
+                                                         const uint32_t* __restrict__ ksk,
+                                                         uint32_t* __restrict__ out, int N, int n, int basebit,
+                                                         int t, int stride) {
+  extern __shared__ uint32_t rows[];  // compacted list of non-zero row indices, capacity N*t
+  __shared__ int nrows;
+  const long long g = blockIdx.x;
+  const uint32_t* src = lwe_in + (size_t)g * (N + 1);
+  if (threadIdx.x == 0) nrows = 0;
+  __syncthreads();
+  const uint32_t prec = 1u << (32 - (1 + basebit * t));
+  const uint32_t mask = (1u << basebit) - 1u;
+  const int base = 1 << basebit;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    const uint32_t abar = src[i] + prec;
+    for (int j = 0; j < t; j++) {
+      const uint32_t k = (abar >> (32 - (j + 1) * basebit)) & mask;
+      if (k != 0) rows[atomicAdd(&nrows, 1)] = (uint32_t)(base * t * i + base * j) + k;
+    }
+  }
+  __syncthreads();
+  const int cnt = nrows;
+  const int ncol4 = stride / 4;
+  for (int c4 = threadIdx.x; c4 < ncol4; c4 += blockDim.x) {
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+    int r = 0;
+    for (; r + 8 <= cnt; r += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        v[u] = __ldg(reinterpret_cast<const uint4*>(ksk + (size_t)rows[r + u] * stride) + c4);
+#pragma unroll
+      for (int u = 0; u < 8; u++) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; r < cnt; r++) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(ksk + (size_t)rows[r] * stride) + c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    uint32_t* o = out + (size_t)g * (n + 1);
+    const int c = c4 * 4;
+    const uint32_t bterm = src[N];
+    if (c + 0 <= n) o[c + 0] = (c + 0 == n ? bterm : 0u) - acc.x;
+    if (c + 1 <= n) o[c + 1] = (c + 1 == n ? bterm : 0u) - acc.y;
+    if (c + 2 <= n) o[c + 2] = (c + 2 == n ? bterm : 0u) - acc.z;
+    if (c + 3 <= n) o[c + 3] = (c + 3 == n ? bterm : 0u) - acc.w;
+  }
+}
+
+// ksk [rows][n+1] -> [rows][stride], zero padded
+__global__ void ksk_repack_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int n1, int stride) {
+  const size_t r = blockIdx.x;
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[r * stride + i] = (i < n1) ? src[r * n1 + i] : 0u;
+}
+
+// Bootstrapping key: reference FourierPoly layout -> engine layout.
+//   src: [polys][N] doubles, poly = (i*2L + r)*2 + ab, groups of (4 re, 4 im): complex index k has
+//        re at (k/4)*8 + k%4 and im at (k/4)*8 + 4 + k%4   (poly/poly.go:54-62)
+//   dst: [polys][8][T] double2, spectrum position k = 8*tau + e stored at [e][tau], scaled by 1/M
+//        (the inverse transform's 1/(N/2), fourier_transform.go:318-346; a power of two, exact).
+__global__ void bsk_repack_kernel(const double* __restrict__ src, double2* __restrict__ dst, int N) {
+  const int M = N / 2, T = M / 8;
+  const size_t poly = blockIdx.x;
+  const double scale = 1.0 / (double)M;
+  for (int k = threadIdx.x; k < M; k += blockDim.x) {
+    const double re = src[poly * N + (k >> 2) * 8 + (k & 3)];
+    const double im = src[poly * N + (k >> 2) * 8 + 4 + (k & 3)];
+    const int tau = k >> 3, e = k & 7;
+    dst[poly * M + e * T + tau] = make_double2(re * scale, im * scale);
+  }
+}
+
+}  // namespace tfhe

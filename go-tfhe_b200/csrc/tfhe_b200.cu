@@ -1,0 +1,609 @@
+// tfhe_b200.cu — context, key upload and the C ABI of include/tfhe_b200.h.
+// Host side of the engine: owns device memory, launches the kernels of blind_rotate.cuh and
+// lwe_kernels.cuh.  No CPU fallback anywhere: if CUDA is unavailable every call fails.
+#include "../../include/tfhe_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "blind_rotate.cuh"
+#include "lwe_kernels.cuh"
+
+using namespace tfhe;
+
+namespace {
+
+std::string g_create_error;
+std::mutex g_create_mu;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct tfhe_ctx {
+  tfhe_params P{};
+  int device = 0;
+  int logN = 0;
+  int variant = -1;          // index into the kernel instantiation table
+  uint32_t offset = 0;
+  bool key_loaded = false, has_ksk = false;
+  double2* d_bsk = nullptr;  // [n][2L][2][8][T]
+  uint32_t* d_ksk = nullptr; // [N*t*base][ksk_stride]
+  uint32_t* d_testvec = nullptr;
+  double2* d_tw = nullptr;
+  int ksk_stride = 0;
+  Tw4 tw0{};
+  cudaStream_t stream = nullptr;  // used by the host-buffer API
+  DevBuf prep, lwe1, tmp, prep2, idx_a, idx_b, ops_dev;       // engine scratch
+  DevBuf h2d_a, h2d_b, h2d_c, h2d_luts, d2h_out, key_stage;   // staging for the host-buffer API
+  int64_t launches = 0;
+  int sm_count = 0;
+  std::string err;
+  // optional per-stage timing (tfhe_ctx_set_timing): CUDA events on the launching stream
+  bool timing = false;
+  struct StageEv { cudaEvent_t e0, e1, e2; };
+  std::vector<StageEv> ev_live, ev_free;
+};
+
+namespace {
+
+int fail(tfhe_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  else { std::lock_guard<std::mutex> l(g_create_mu); g_create_error = buf; }
+  return code;
+}
+#define CK(c, call)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e__ = (call);                                                                         \
+    if (e__ != cudaSuccess) return fail((c), TFHE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+  } while (0)
+
+// S(m, i): twiddle of block i at the stage with m blocks — the square root the reference tabulates
+// as tw[m-1+i] (poly/poly_evaluator.go:114-143): exp(-2 pi i rev(i)/M) * exp(i pi / (4m)), rev = bit
+// reversal over log2(M/2) bits.  Evaluated in long double and rounded once.
+double2 twiddle(int M, int m, int i) {
+  int bits = 0;
+  while ((1 << bits) < M / 2) bits++;
+  int r = 0;
+  for (int b = 0; b < bits; b++)
+    if (i & (1 << b)) r |= 1 << (bits - 1 - b);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  long double ang = -2.0L * pi * (long double)r / (long double)M + pi / (4.0L * (long double)m);
+  return make_double2((double)cosl(ang), (double)sinl(ang));
+}
+Tw4 block_twiddles(int M, int m, int i) {
+  Tw4 t;
+  t.s[0] = twiddle(M, m, i);
+  t.s[1] = (2 * m <= M / 2) ? twiddle(M, 2 * m, 2 * i) : make_double2(1, 0);
+  t.s[2] = (4 * m <= M / 2) ? twiddle(M, 4 * m, 4 * i) : make_double2(1, 0);
+  t.s[3] = (4 * m <= M / 2) ? twiddle(M, 4 * m, 4 * i + 2) : make_double2(1, 0);
+  return t;
+}
+template <int LOGM>
+void build_twiddles(Tw4& tw0, std::vector<Tw4>& tab) {
+  using G = Geo<LOGM>;
+  tw0 = block_twiddles(G::M, 1, 0);
+  tab.assign(G::tab_len() > 0 ? G::tab_len() : 1, Tw4{});
+  for (int k = 1; k < G::NPASS; k++) {
+    const int m = (k < G::NFULL) ? (1 << (3 * k)) : G::T;  // partial pass: virtual (m, i) = (M/8, tau)
+    for (int i = 0; i < G::blocks(k); i++) tab[G::tab_off(k) + i] = block_twiddles(G::M, m, i);
+  }
+}
+
+// ---- kernel instantiation table ---------------------------------------------------------------
+struct Variant {
+  int logN, L, bgbit;
+  bool small;
+  void (*br)(const BrArgs);
+  void (*cmux)(const CmuxArgs);
+  size_t (*br_smem)(int n);
+};
+template <int LOGN> size_t br_smem(int n) { return br_smem_bytes<LOGN>(n); }
+#define VARIANT(LOGN, L, BG, SMALL, MINB)                                                         \
+  { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>, cmux_kernel<LOGN, L, BG, SMALL, MINB>, \
+    br_smem<LOGN> }
+const Variant kVariants[] = {
+    VARIANT(10, 3, 6, true, 4),    // 80 / 110 / 128-bit  (params/params.go:83-180)
+    VARIANT(10, 2, 10, false, 4),  // Uint1               (params.go:194-223)
+    VARIANT(9, 1, 18, false, 8),   // Uint2               (params.go:236-265)
+    VARIANT(10, 1, 23, false, 4),  // Uint3               (params.go:277-306)
+    VARIANT(11, 1, 22, false, 2),  // Uint4 / Uint5       (params.go:318-391)
+};
+
+int find_variant(const tfhe_params& P) {
+  int logN = 0;
+  while ((1 << logN) < P.N) logN++;
+  if ((1 << logN) != P.N) return -1;
+  for (size_t v = 0; v < sizeof(kVariants) / sizeof(kVariants[0]); v++)
+    if (kVariants[v].logN == logN && kVariants[v].L == P.L && kVariants[v].bgbit == P.bgbit) return (int)v;
+  return -1;
+}
+
+size_t cmux_smem(int N) { return (size_t)8 * N + (size_t)16 * N + (size_t)8 * N; }
+
+int set_device(tfhe_ctx* c) {
+  CK(c, cudaSetDevice(c->device));
+  return 0;
+}
+
+// --- engine steps on device buffers --------------------------------------------------------------
+int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const uint32_t* d_luts, int64_t nluts,
+                        uint32_t* d_out, int out_mode, cudaStream_t s) {
+  if (count == 0) return 0;
+  const Variant& V = kVariants[c->variant];
+  BrArgs a{};
+  a.ct_in = d_ct; a.testvec = c->d_testvec; a.luts = d_luts; a.nluts = nluts; a.bsk = c->d_bsk; a.tw_tab = c->d_tw;
+  a.out = d_out; a.n = c->P.n; a.offset = c->offset; a.out_mode = out_mode; a.tw0 = c->tw0;
+  const int T = c->P.N / 16;
+  V.br<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  return 0;
+}
+
+int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s) {
+  if (count == 0) return 0;
+  const size_t sm = (size_t)c->P.N * c->P.iks_t * sizeof(uint32_t);
+  key_switch_kernel<<<(unsigned)count, 256, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
+                                                     c->P.iks_t, c->ksk_stride);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  return 0;
+}
+
+int check_ready(tfhe_ctx* c, bool need_ksk) {
+  if (!c) return TFHE_ERR_ARG;
+  if (!c->key_loaded) return fail(c, TFHE_ERR_STATE, "cloud key not loaded");
+  if (need_ksk && !c->has_ksk) return fail(c, TFHE_ERR_STATE, "key-switching key not loaded");
+  return 0;
+}
+
+int bootstrap_device(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const uint32_t* d_luts, int64_t nluts,
+                     uint32_t* d_out, cudaStream_t s) {
+  CK(c, c->lwe1.reserve((size_t)count * (c->P.N + 1) * 4));
+  tfhe_ctx::StageEv ev{};
+  if (c->timing && count > 0) {
+    if (!c->ev_free.empty()) { ev = c->ev_free.back(); c->ev_free.pop_back(); }
+    else { CK(c, cudaEventCreate(&ev.e0)); CK(c, cudaEventCreate(&ev.e1)); CK(c, cudaEventCreate(&ev.e2)); }
+    CK(c, cudaEventRecord(ev.e0, s));
+  }
+  int rc = launch_blind_rotate(c, count, d_ct, d_luts, nluts, c->lwe1.as<uint32_t>(), 1, s);
+  if (rc) return rc;
+  if (c->timing && count > 0) CK(c, cudaEventRecord(ev.e1, s));
+  rc = launch_key_switch(c, count, c->lwe1.as<uint32_t>(), d_out, s);
+  if (rc) return rc;
+  if (c->timing && count > 0) { CK(c, cudaEventRecord(ev.e2, s)); c->ev_live.push_back(ev); }
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* tfhe_version(void) { return "tfhe_b200 0.1 (sm_100a)"; }
+
+const char* tfhe_last_error(const tfhe_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  std::lock_guard<std::mutex> l(g_create_mu);
+  return g_create_error.c_str();
+}
+
+int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
+  if (!params || !out) return fail(nullptr, TFHE_ERR_ARG, "null argument");
+  *out = nullptr;
+  const tfhe_params& P = *params;
+  if (P.n <= 0 || P.n > 4096 || P.L <= 0 || P.bgbit <= 0 || P.L * P.bgbit > 32 || P.basebit <= 0 || P.iks_t <= 0 ||
+      P.basebit * P.iks_t > 31)
+    return fail(nullptr, TFHE_ERR_ARG, "invalid parameters");
+  const int v = find_variant(P);
+  if (v < 0)
+    return fail(nullptr, TFHE_ERR_ARG, "unsupported shape N=%d L=%d bgbit=%d (supported: the reference's 80/110/128-bit and Uint1-5 sets)",
+                P.N, P.L, P.bgbit);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, TFHE_ERR_CUDA, "no CUDA device (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return fail(nullptr, TFHE_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return fail(nullptr, TFHE_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, TFHE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                prop.minor);
+  tfhe_ctx* c = new (std::nothrow) tfhe_ctx();
+  if (!c) return fail(nullptr, TFHE_ERR_NOMEM, "out of host memory");
+  c->P = P; c->device = device; c->variant = v; c->logN = kVariants[v].logN; c->sm_count = prop.multiProcessorCount;
+  auto bail = [&](const char* what, cudaError_t err) {
+    int rc = fail(nullptr, TFHE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+    tfhe_ctx_destroy(c);
+    return rc;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  std::vector<Tw4> tab;
+  switch (c->logN) {
+    case 9: build_twiddles<8>(c->tw0, tab); break;
+    case 10: build_twiddles<9>(c->tw0, tab); break;
+    case 11: build_twiddles<10>(c->tw0, tab); break;
+    default: tfhe_ctx_destroy(c); return fail(nullptr, TFHE_ERR_ARG, "unsupported N");
+  }
+  if ((e = cudaMalloc(&c->d_tw, tab.size() * sizeof(Tw4))) != cudaSuccess) return bail("cudaMalloc(twiddles)", e);
+  if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return bail("cudaMemcpy(twiddles)", e);
+  const Variant& V = kVariants[v];
+  if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(P.n))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate)", e);
+  if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(cmux)", e);
+  if ((e = cudaFuncSetAttribute(key_switch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((size_t)P.N * P.iks_t * 4))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(key_switch)", e);
+  *out = c;
+  return TFHE_OK;
+}
+
+void tfhe_ctx_destroy(tfhe_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  for (DevBuf* b : {&c->prep, &c->lwe1, &c->tmp, &c->prep2, &c->idx_a, &c->idx_b, &c->ops_dev, &c->h2d_a, &c->h2d_b,
+                    &c->h2d_c, &c->h2d_luts, &c->d2h_out, &c->key_stage})
+    b->release();
+  for (auto* v : {&c->ev_live, &c->ev_free})
+    for (auto& ev : *v) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); cudaEventDestroy(ev.e2); }
+  if (c->d_bsk) cudaFree(c->d_bsk);
+  if (c->d_ksk) cudaFree(c->d_ksk);
+  if (c->d_testvec) cudaFree(c->d_testvec);
+  if (c->d_tw) cudaFree(c->d_tw);
+  delete c;
+}
+
+int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_bsk_fft, const uint32_t* d_ksk,
+                                  const uint32_t* d_testvec, void* stream) {
+  if (!c || !d_bsk_fft || !d_testvec) return fail(c, TFHE_ERR_ARG, "null argument");
+  int rc = set_device(c);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const tfhe_params& P = c->P;
+  const size_t polys = (size_t)P.n * 2 * P.L * 2;
+  const int M = P.N / 2;
+  if (!c->d_bsk) CK(c, cudaMalloc(&c->d_bsk, polys * M * sizeof(double2)));
+  if (!c->d_testvec) CK(c, cudaMalloc(&c->d_testvec, (size_t)2 * P.N * 4));
+  bsk_repack_kernel<<<(unsigned)polys, 128, 0, s>>>(d_bsk_fft, c->d_bsk, P.N);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  CK(c, cudaMemcpyAsync(c->d_testvec, d_testvec, (size_t)2 * P.N * 4, cudaMemcpyDeviceToDevice, s));
+  if (d_ksk) {
+    const size_t rows = (size_t)P.N * P.iks_t * (1u << P.basebit);
+    c->ksk_stride = (P.n + 1 + 3) / 4 * 4;
+    if (!c->d_ksk) CK(c, cudaMalloc(&c->d_ksk, rows * c->ksk_stride * 4));
+    ksk_repack_kernel<<<(unsigned)rows, 128, 0, s>>>(d_ksk, c->d_ksk, P.n + 1, c->ksk_stride);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    c->has_ksk = true;
+  }
+  CK(c, cudaStreamSynchronize(s));
+  c->offset = offset;
+  c->key_loaded = true;
+  return TFHE_OK;
+}
+
+int tfhe_ctx_load_cloudkey(tfhe_ctx* c, uint32_t offset, const double* bsk_fft, const uint32_t* ksk,
+                           const uint32_t* testvec) {
+  if (!c || !bsk_fft || !testvec) return fail(c, TFHE_ERR_ARG, "null argument");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const tfhe_params& P = c->P;
+  const size_t bsk_bytes = (size_t)P.n * 2 * P.L * 2 * P.N * sizeof(double);
+  const size_t ksk_bytes = ksk ? (size_t)P.N * P.iks_t * (1u << P.basebit) * (P.n + 1) * 4 : 0;
+  const size_t tv_bytes = (size_t)2 * P.N * 4;
+  // stage the reference-layout key in device memory, repack, then drop the staging copy
+  DevBuf sb, sk, st;
+  CK(c, sb.reserve(bsk_bytes));
+  cudaError_t e = cudaMemcpy(sb.p, bsk_fft, bsk_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && ksk) { e = sk.reserve(ksk_bytes); if (e == cudaSuccess) e = cudaMemcpy(sk.p, ksk, ksk_bytes, cudaMemcpyHostToDevice); }
+  if (e == cudaSuccess) { e = st.reserve(tv_bytes); if (e == cudaSuccess) e = cudaMemcpy(st.p, testvec, tv_bytes, cudaMemcpyHostToDevice); }
+  if (e == cudaSuccess)
+    rc = tfhe_ctx_load_cloudkey_device(c, offset, sb.as<double>(), ksk ? sk.as<uint32_t>() : nullptr, st.as<uint32_t>(),
+                                       c->stream);
+  sb.release(); sk.release(); st.release();
+  if (e != cudaSuccess) return fail(c, TFHE_ERR_CUDA, "key upload: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// ---- device-buffer API ----------------------------------------------------------------------------
+int tfhe_bootstrap_batch_device(tfhe_ctx* c, int64_t count, const uint32_t* d_ct_in, const uint32_t* d_luts,
+                                int64_t nluts, uint32_t* d_ct_out, void* stream) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!d_ct_in || !d_ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (d_luts && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
+  if ((rc = set_device(c))) return rc;
+  return bootstrap_device(c, count, d_ct_in, d_luts, nluts, d_ct_out, (cudaStream_t)stream);
+}
+
+// ops is a HOST array (one byte per gate); ciphertext pointers are device pointers.
+int tfhe_gate_batch_device(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* d_a,
+                           const uint32_t* d_b, const uint32_t* d_c, uint32_t* d_out, void* stream) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  if (count < 0 || !ops || (nops != 1 && nops != count) || (count > 0 && (!d_a || !d_out)))
+    return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (count == 0) return TFHE_OK;
+  if ((rc = set_device(c))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n1 = c->P.n + 1;
+  // classify on the host
+  bool any_mux = false, any_unary = false, any_boot = false;
+  for (int64_t g = 0; g < nops; g++) {
+    const uint8_t op = ops[g];
+    if (op > TFHE_OP_COPY) return fail(c, TFHE_ERR_ARG, "unknown opcode %d at gate %lld", (int)op, (long long)g);
+    if (op == TFHE_OP_MUX) any_mux = true;
+    else if (op >= TFHE_OP_NOT) any_unary = true;
+    else any_boot = true;
+  }
+  if ((any_boot || any_mux) && !d_b) return fail(c, TFHE_ERR_ARG, "b is required by two-input gates");
+  if (any_mux && !d_c) return fail(c, TFHE_ERR_ARG, "c is required by MUX gates");
+  CK(c, c->ops_dev.reserve((size_t)nops));
+  CK(c, cudaMemcpyAsync(c->ops_dev.p, ops, (size_t)nops, cudaMemcpyHostToDevice, s));
+  CK(c, c->prep.reserve((size_t)2 * count * n1 * 4));
+  uint32_t* prep0 = c->prep.as<uint32_t>();
+  uint32_t* prep1 = prep0 + (size_t)count * n1;
+  if (!any_mux && !any_unary) {  // fast path: every gate is one bootstrap, rows stay in place
+    gate_prepare_kernel<<<(unsigned)count, 256, 0, s>>>(count, c->ops_dev.as<uint8_t>(), nops, d_a, d_b, d_c, prep0, prep1,
+                                                        c->P.n);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return bootstrap_device(c, count, prep0, nullptr, 0, d_out, s);
+  }
+  // general path: NOT/COPY results go straight to d_out; bootstrapped jobs are compacted by index lists
+  gate_prepare_kernel<<<(unsigned)count, 256, 0, s>>>(count, c->ops_dev.as<uint8_t>(), nops, d_a, d_b, d_c, d_out, prep1,
+                                                      c->P.n);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  // (prepared rows of two-input gates now sit in d_out[g]; MUX second operand in prep1[g])
+  std::vector<int> src1, dst1, muxg;  // level-1 jobs: src row in the virtual space [d_out | prep1], dst likewise in [d_out | tmp]
+  for (int64_t g = 0; g < count; g++) {
+    const uint8_t op = ops[nops == 1 ? 0 : g];
+    if (op == TFHE_OP_MUX) { muxg.push_back((int)g); }
+    else if (op < TFHE_OP_MUX) { src1.push_back((int)g); }
+  }
+  const int64_t nb = (int64_t)src1.size(), nm = (int64_t)muxg.size();
+  const int64_t j1 = nb + 2 * nm;
+  // gather level-1 inputs into a contiguous batch: [plain gates | mux AND(a,b) | mux ANDNY(a,c)]
+  CK(c, c->prep2.reserve((size_t)(j1 > 0 ? j1 : 1) * n1 * 4));
+  CK(c, c->tmp.reserve((size_t)(j1 > 0 ? j1 : 1) * n1 * 4));
+  CK(c, c->idx_a.reserve((size_t)(count + 1) * sizeof(int)));
+  CK(c, c->idx_b.reserve((size_t)(count + 1) * sizeof(int)));
+  uint32_t* in1 = c->prep2.as<uint32_t>();
+  uint32_t* out1 = c->tmp.as<uint32_t>();
+  if (nb) {
+    CK(c, cudaMemcpyAsync(c->idx_a.p, src1.data(), nb * sizeof(int), cudaMemcpyHostToDevice, s));
+    gather_rows_kernel<<<(unsigned)nb, 128, 0, s>>>(d_out, c->idx_a.as<int>(), in1, n1);
+    c->launches++;
+  }
+  if (nm) {
+    CK(c, cudaMemcpyAsync(c->idx_b.p, muxg.data(), nm * sizeof(int), cudaMemcpyHostToDevice, s));
+    gather_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(d_out, c->idx_b.as<int>(), in1 + (size_t)nb * n1, n1);
+    gather_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(prep1, c->idx_b.as<int>(), in1 + (size_t)(nb + nm) * n1, n1);
+    c->launches += 2;
+  }
+  CK(c, cudaGetLastError());
+  if ((rc = bootstrap_device(c, j1, in1, nullptr, 0, out1, s))) return rc;
+  if (nb) {
+    scatter_rows_kernel<<<(unsigned)nb, 128, 0, s>>>(out1, c->idx_a.as<int>(), d_out, n1);
+    c->launches++;
+  }
+  if (nm) {  // level 2: OR(andAB, andNotAC)
+    uint32_t* in2 = in1;  // reuse
+    uint8_t dummy = 0; (void)dummy;
+    mux_or_prepare_kernel<<<(unsigned)nm, 256, 0, s>>>(nm, nullptr, 0, out1 + (size_t)nb * n1, out1 + (size_t)(nb + nm) * n1,
+                                                       in2, c->P.n);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    uint32_t* out2 = out1;  // level-1 outputs are consumed by now (stream order)
+    if ((rc = bootstrap_device(c, nm, in2, nullptr, 0, out2, s))) return rc;
+    scatter_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(out2, c->idx_b.as<int>(), d_out, n1);
+    c->launches++;
+  }
+  CK(c, cudaGetLastError());
+  // index vectors are host temporaries consumed by async copies: make sure the copies are done
+  CK(c, cudaStreamSynchronize(s));
+  return TFHE_OK;
+}
+
+// ---- host-buffer API --------------------------------------------------------------------------------
+static int h2d(tfhe_ctx* c, DevBuf& b, const void* src, size_t bytes) {
+  CK(c, b.reserve(bytes));
+  CK(c, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return 0;
+}
+
+int tfhe_bootstrap_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* luts, int64_t nluts,
+                         uint32_t* ct_out) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!ct_in || !ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (luts && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
+  if (count == 0) return TFHE_OK;
+  if ((rc = set_device(c))) return rc;
+  const size_t bytes = (size_t)count * (c->P.n + 1) * 4;
+  if ((rc = h2d(c, c->h2d_a, ct_in, bytes))) return rc;
+  if (luts && (rc = h2d(c, c->h2d_luts, luts, (size_t)nluts * 2 * c->P.N * 4))) return rc;
+  CK(c, c->d2h_out.reserve(bytes));
+  if ((rc = bootstrap_device(c, count, c->h2d_a.as<uint32_t>(), luts ? c->h2d_luts.as<uint32_t>() : nullptr, nluts,
+                             c->d2h_out.as<uint32_t>(), c->stream)))
+    return rc;
+  CK(c, cudaMemcpyAsync(ct_out, c->d2h_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+int tfhe_gate_batch(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* a, const uint32_t* b,
+                    const uint32_t* cc, uint32_t* out) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  if (count < 0 || !ops || (nops != 1 && nops != count) || (count > 0 && (!a || !out)))
+    return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (count == 0) return TFHE_OK;
+  if ((rc = set_device(c))) return rc;
+  const size_t bytes = (size_t)count * (c->P.n + 1) * 4;
+  if ((rc = h2d(c, c->h2d_a, a, bytes))) return rc;
+  if (b && (rc = h2d(c, c->h2d_b, b, bytes))) return rc;
+  if (cc && (rc = h2d(c, c->h2d_c, cc, bytes))) return rc;
+  CK(c, c->d2h_out.reserve(bytes));
+  if ((rc = tfhe_gate_batch_device(c, count, ops, nops, c->h2d_a.as<uint32_t>(), b ? c->h2d_b.as<uint32_t>() : nullptr,
+                                   cc ? c->h2d_c.as<uint32_t>() : nullptr, c->d2h_out.as<uint32_t>(), c->stream)))
+    return rc;
+  CK(c, cudaMemcpyAsync(out, c->d2h_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+int tfhe_blind_rotate_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* luts, int64_t nluts,
+                            uint32_t* trlwe_out) {
+  int rc = check_ready(c, false);
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!ct_in || !trlwe_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (luts && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
+  if (count == 0) return TFHE_OK;
+  if ((rc = set_device(c))) return rc;
+  const size_t in_bytes = (size_t)count * (c->P.n + 1) * 4, out_bytes = (size_t)count * 2 * c->P.N * 4;
+  if ((rc = h2d(c, c->h2d_a, ct_in, in_bytes))) return rc;
+  if (luts && (rc = h2d(c, c->h2d_luts, luts, (size_t)nluts * 2 * c->P.N * 4))) return rc;
+  CK(c, c->d2h_out.reserve(out_bytes));
+  if ((rc = launch_blind_rotate(c, count, c->h2d_a.as<uint32_t>(), luts ? c->h2d_luts.as<uint32_t>() : nullptr, nluts,
+                                c->d2h_out.as<uint32_t>(), 0, c->stream)))
+    return rc;
+  CK(c, cudaMemcpyAsync(trlwe_out, c->d2h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+int tfhe_cmux_batch(tfhe_ctx* c, int64_t count, int32_t bsk_index, const uint32_t* ct0, const uint32_t* ct1,
+                    uint32_t* out) {
+  int rc = check_ready(c, false);
+  if (rc) return rc;
+  if (count < 0 || bsk_index < 0 || bsk_index >= c->P.n || (count > 0 && (!ct1 || !out)))
+    return fail(c, TFHE_ERR_ARG, "bad cmux arguments");
+  if (count == 0) return TFHE_OK;
+  if ((rc = set_device(c))) return rc;
+  const size_t bytes = (size_t)count * 2 * c->P.N * 4;
+  if (ct0 && (rc = h2d(c, c->h2d_a, ct0, bytes))) return rc;
+  if ((rc = h2d(c, c->h2d_b, ct1, bytes))) return rc;
+  CK(c, c->d2h_out.reserve(bytes));
+  const Variant& V = kVariants[c->variant];
+  CmuxArgs a{};
+  a.ct0 = ct0 ? c->h2d_a.as<uint32_t>() : nullptr;
+  a.ct1 = c->h2d_b.as<uint32_t>();
+  a.bsk_row = c->d_bsk + (size_t)bsk_index * 2 * c->P.L * 2 * (c->P.N / 2);
+  a.tw_tab = c->d_tw; a.out = c->d2h_out.as<uint32_t>(); a.offset = c->offset; a.tw0 = c->tw0;
+  V.cmux<<<(unsigned)count, c->P.N / 16, cmux_smem(c->P.N), c->stream>>>(a);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  CK(c, cudaMemcpyAsync(out, c->d2h_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+int tfhe_sample_extract_batch(tfhe_ctx* c, int64_t count, const uint32_t* trlwe_in, uint32_t* lwe_out) {
+  if (!c) return TFHE_ERR_ARG;
+  if (count < 0 || (count > 0 && (!trlwe_in || !lwe_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (count == 0) return TFHE_OK;
+  int rc = set_device(c);
+  if (rc) return rc;
+  const size_t in_bytes = (size_t)count * 2 * c->P.N * 4, out_bytes = (size_t)count * (c->P.N + 1) * 4;
+  if ((rc = h2d(c, c->h2d_a, trlwe_in, in_bytes))) return rc;
+  CK(c, c->d2h_out.reserve(out_bytes));
+  sample_extract_kernel<<<(unsigned)count, 256, 0, c->stream>>>(c->h2d_a.as<uint32_t>(), c->d2h_out.as<uint32_t>(), c->P.N);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  CK(c, cudaMemcpyAsync(lwe_out, c->d2h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+int tfhe_key_switch_batch(tfhe_ctx* c, int64_t count, const uint32_t* lwe_in, uint32_t* ct_out) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  if (count < 0 || (count > 0 && (!lwe_in || !ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (count == 0) return TFHE_OK;
+  if ((rc = set_device(c))) return rc;
+  const size_t in_bytes = (size_t)count * (c->P.N + 1) * 4, out_bytes = (size_t)count * (c->P.n + 1) * 4;
+  if ((rc = h2d(c, c->h2d_a, lwe_in, in_bytes))) return rc;
+  CK(c, c->d2h_out.reserve(out_bytes));
+  if ((rc = launch_key_switch(c, count, c->h2d_a.as<uint32_t>(), c->d2h_out.as<uint32_t>(), c->stream))) return rc;
+  CK(c, cudaMemcpyAsync(ct_out, c->d2h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) { return c ? c->launches : 0; }
+
+int tfhe_ctx_set_timing(tfhe_ctx* c, int enable) {
+  if (!c) return TFHE_ERR_ARG;
+  c->timing = enable != 0;
+  return TFHE_OK;
+}
+
+int tfhe_ctx_collect_timing(tfhe_ctx* c, double out[4]) {
+  if (!c || !out) return TFHE_ERR_ARG;
+  int rc = set_device(c);
+  if (rc) return rc;
+  out[0] = out[1] = out[2] = out[3] = 0.0;
+  for (auto& ev : c->ev_live) {
+    CK(c, cudaEventSynchronize(ev.e2));
+    float a = 0.f, b = 0.f;
+    CK(c, cudaEventElapsedTime(&a, ev.e0, ev.e1));
+    CK(c, cudaEventElapsedTime(&b, ev.e1, ev.e2));
+    out[0] += a; out[1] += 1.0; out[2] += b; out[3] += 1.0;
+    c->ev_free.push_back(ev);
+  }
+  c->ev_live.clear();
+  return TFHE_OK;
+}
+
+int64_t tfhe_ctx_algorithmic_bytes_per_bootstrap(const tfhe_ctx* c) {
+  if (!c) return 0;
+  const tfhe_params& P = c->P;
+  const int64_t base = 1ll << P.basebit;
+  const int64_t bk = (int64_t)P.n * 2 * P.L * 2 * P.N * 8;
+  const int64_t ks = (int64_t)P.N * P.iks_t * (base - 1) / base * (P.n + 1) * 4;
+  const int64_t io = (int64_t)3 * (P.n + 1) * 4;
+  return bk + ks + io;
+}
+
+}  // extern "C"

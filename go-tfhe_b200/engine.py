@@ -1,0 +1,165 @@
+"""Context: owns one tfhe_ctx (one GPU).  Thin, typed wrapper over the C ABI; all compute happens in
+libtfhe_b200.so.  numpy arrays in / out for the host-buffer entry points, raw device pointers (ints,
+e.g. torch.Tensor.data_ptr()) for the *_device entry points."""
+import ctypes
+
+import numpy as np
+
+from . import _native
+from .params import ParamSet
+
+OPCODES = {"NAND": 0, "AND": 1, "OR": 2, "XOR": 3, "XNOR": 4, "NOR": 5, "ANDNY": 6, "ANDYN": 7, "ORNY": 8, "ORYN": 9,
+           "MUX": 10, "NOT": 11, "COPY": 12}
+
+
+class TfheError(RuntimeError):
+    pass
+
+
+def _u32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    return a if shape is None else a.reshape(shape)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _ops(ops, count):
+    if isinstance(ops, (str, int)):
+        ops = [ops]
+    v = np.array([OPCODES[o.upper()] if isinstance(o, str) else int(o) for o in ops], dtype=np.uint8)
+    if len(v) not in (1, count):
+        raise ValueError("ops must have length 1 or count")
+    return v
+
+
+class Context:
+    def __init__(self, P: ParamSet, device=0):
+        self.P = P
+        self.lib = _native.engine()
+        self.h = ctypes.c_void_p()
+        tp = _native.TfheParams(P.n, P.N, P.L, P.BGBIT, P.BASEBIT, P.IKS_T)
+        rc = self.lib.tfhe_ctx_create(ctypes.byref(tp), int(device), ctypes.byref(self.h))
+        if rc != 0:
+            raise TfheError("tfhe_ctx_create: %s" % self.lib.tfhe_last_error(None).decode())
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.tfhe_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise TfheError("%s failed (%d): %s" % (what, rc, self.lib.tfhe_last_error(self.h).decode()))
+
+    # --- keys ---------------------------------------------------------------------------------------
+    def load_cloudkey(self, offset, bsk_fft, ksk, testvec):
+        P = self.P
+        bsk = np.ascontiguousarray(bsk_fft, dtype=np.float64)
+        assert bsk.size == P.n * 2 * P.L * 2 * P.N, "bsk_fft must be [n][2L][2][N]"
+        k = None
+        if ksk is not None:
+            k = _u32(ksk)
+            assert k.size == P.ksk_rows * (P.n + 1), "ksk must be [N][t][base][n+1]"
+        tv = _u32(testvec)
+        assert tv.size == 2 * P.N
+        self._ck(self.lib.tfhe_ctx_load_cloudkey(self.h, ctypes.c_uint32(offset), _ptr(bsk), _ptr(k), _ptr(tv)),
+                 "tfhe_ctx_load_cloudkey")
+
+    def load_cloudkey_device(self, offset, d_bsk_fft, d_ksk, d_testvec, stream=0):
+        self._ck(self.lib.tfhe_ctx_load_cloudkey_device(self.h, ctypes.c_uint32(offset), d_bsk_fft, d_ksk, d_testvec,
+                                                        stream), "tfhe_ctx_load_cloudkey_device")
+
+    # --- host-buffer hot path -----------------------------------------------------------------------
+    def bootstrap_batch(self, ct_in, luts=None):
+        P = self.P
+        ct = _u32(ct_in, (-1, P.n + 1))
+        out = np.empty_like(ct)
+        l, nl = None, 0
+        if luts is not None:
+            l = _u32(luts, (-1, 2 * P.N))
+            nl = len(l)
+        self._ck(self.lib.tfhe_bootstrap_batch(self.h, len(ct), _ptr(ct), _ptr(l), nl, _ptr(out)), "tfhe_bootstrap_batch")
+        return out
+
+    def gate_batch(self, ops, a, b=None, c=None):
+        P = self.P
+        a = _u32(a, (-1, P.n + 1))
+        b = None if b is None else _u32(b, (-1, P.n + 1))
+        c = None if c is None else _u32(c, (-1, P.n + 1))
+        ov = _ops(ops, len(a))
+        out = np.empty_like(a)
+        self._ck(self.lib.tfhe_gate_batch(self.h, len(a), _ptr(ov), len(ov), _ptr(a), _ptr(b), _ptr(c), _ptr(out)),
+                 "tfhe_gate_batch")
+        return out
+
+    def blind_rotate_batch(self, ct_in, luts=None):
+        P = self.P
+        ct = _u32(ct_in, (-1, P.n + 1))
+        out = np.empty((len(ct), 2, P.N), dtype=np.uint32)
+        l, nl = None, 0
+        if luts is not None:
+            l = _u32(luts, (-1, 2 * P.N))
+            nl = len(l)
+        self._ck(self.lib.tfhe_blind_rotate_batch(self.h, len(ct), _ptr(ct), _ptr(l), nl, _ptr(out)),
+                 "tfhe_blind_rotate_batch")
+        return out
+
+    def cmux_batch(self, bsk_index, ct0, ct1):
+        P = self.P
+        ct1 = _u32(ct1, (-1, 2 * P.N))
+        ct0 = None if ct0 is None else _u32(ct0, (-1, 2 * P.N))
+        out = np.empty_like(ct1)
+        self._ck(self.lib.tfhe_cmux_batch(self.h, len(ct1), int(bsk_index), _ptr(ct0), _ptr(ct1), _ptr(out)),
+                 "tfhe_cmux_batch")
+        return out.reshape(-1, 2, P.N)
+
+    def sample_extract_batch(self, trlwe):
+        P = self.P
+        t = _u32(trlwe, (-1, 2 * P.N))
+        out = np.empty((len(t), P.N + 1), dtype=np.uint32)
+        self._ck(self.lib.tfhe_sample_extract_batch(self.h, len(t), _ptr(t), _ptr(out)), "tfhe_sample_extract_batch")
+        return out
+
+    def key_switch_batch(self, lwe1):
+        P = self.P
+        x = _u32(lwe1, (-1, P.N + 1))
+        out = np.empty((len(x), P.n + 1), dtype=np.uint32)
+        self._ck(self.lib.tfhe_key_switch_batch(self.h, len(x), _ptr(x), _ptr(out)), "tfhe_key_switch_batch")
+        return out
+
+    # --- device-buffer hot path (pointers are ints) ---------------------------------------------------
+    def bootstrap_batch_device(self, count, d_ct_in, d_ct_out, d_luts=None, nluts=0, stream=0):
+        self._ck(self.lib.tfhe_bootstrap_batch_device(self.h, count, d_ct_in, d_luts, nluts, d_ct_out, stream),
+                 "tfhe_bootstrap_batch_device")
+
+    def gate_batch_device(self, count, ops, d_a, d_b, d_c, d_out, stream=0):
+        ov = _ops(ops, count)
+        self._ck(self.lib.tfhe_gate_batch_device(self.h, count, _ptr(ov), len(ov), d_a, d_b, d_c, d_out, stream),
+                 "tfhe_gate_batch_device")
+
+    def set_timing(self, enable=True):
+        self._ck(self.lib.tfhe_ctx_set_timing(self.h, 1 if enable else 0), "tfhe_ctx_set_timing")
+
+    def collect_timing(self):
+        """{'blind_rotate_ms', 'blind_rotate_launches', 'key_switch_ms', 'key_switch_launches'} since last collect."""
+        out = (ctypes.c_double * 4)()
+        self._ck(self.lib.tfhe_ctx_collect_timing(self.h, ctypes.byref(out)), "tfhe_ctx_collect_timing")
+        return {"blind_rotate_ms": out[0], "blind_rotate_launches": int(out[1]), "key_switch_ms": out[2],
+                "key_switch_launches": int(out[3])}
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.tfhe_ctx_kernel_launches(self.h))
+
+    @property
+    def algorithmic_bytes_per_bootstrap(self):
+        return int(self.lib.tfhe_ctx_algorithmic_bytes_per_bootstrap(self.h))

@@ -1,0 +1,153 @@
+/*
+ * tfhe_b200.h — C ABI of the B200-native TFHE gate-bootstrap engine.
+ *
+ * This is the drop-in boundary for the hot path of thedonutfactory/go-tfhe (reference paths
+ * below are relative to the reference repository).  The reference has no FFI of its own — it
+ * is a single Go module — so the boundary is cut at the narrowest waist of its call graph:
+ * flattened ciphertext batches in, flattened ciphertext batches out, cloud key resident on the
+ * device.  A thin cgo shim (go/) flattens the reference's pointer-rich Go
+ * types into these buffers and keeps the gates.* / evaluator.* signatures unchanged.
+ *
+ * Conventions
+ *   - All functions return 0 on success and a negative tfhe_status on failure; the message is
+ *     available from tfhe_last_error().  (The reference panics; the Go shim re-panics.)
+ *   - Host buffers are caller-owned, contiguous, and borrowed only for the duration of a call.
+ *   - One call at a time per context.  One context per GPU (one process per GPU in multi-GPU
+ *     runs; gates shard by index, keys are replicated, no collective on the hot path).
+ *   - There is no CPU fallback: every entry point fails with TFHE_ERR_CUDA if no sm_100 device.
+ *
+ * Flattened layouts (Torus = uint32_t, reference params/params.go:27)
+ *   LWE ciphertext batch   [count][n+1]          tlwe.TLWELv0.P               tlwe/tlwe.go:11-13
+ *   TRLWE / LUT batch      [count][2][N]         trlwe.TRLWELv1 {A,B}         trlwe/trlwe.go:13-16
+ *   key-switching key      [N][t][base][n+1]     CloudKey.KeySwitchingKey, row index
+ *                                                base*t*i + base*j + k        cloudkey/cloudkey.go:111
+ *   bootstrapping key      [n][2L][2][N] double  CloudKey.BootstrappingKey[i].TRLWEFFT[r].{A,B}
+ *                                                in the reference FourierPoly layout (groups of
+ *                                                4 real then 4 imaginary parts)
+ *                                                trgsw/trgsw.go:60-68, poly/poly.go:54-62
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfhe_ctx tfhe_ctx;
+
+/* Mirrors params.TLWELv0Params.N and params.TRGSWLv1Params{N,L,BGBIT,BASEBIT,IKS_T}
+ * (params/params.go:50-78).  Supported shapes: N in {512,1024,2048}, L*bgbit <= 32. */
+typedef struct {
+  int32_t n;       /* LWE dimension (TLWELv0.N)            */
+  int32_t N;       /* ring degree   (TRGSWLv1.N)           */
+  int32_t L;       /* gadget levels (TRGSWLv1.L)           */
+  int32_t bgbit;   /* log2 gadget base (TRGSWLv1.BGBIT)    */
+  int32_t basebit; /* log2 key-switch base (BASEBIT)       */
+  int32_t iks_t;   /* key-switch levels (IKS_T)            */
+} tfhe_params;
+
+typedef enum {
+  TFHE_OK = 0,
+  TFHE_ERR_ARG = -1,     /* bad argument / unsupported parameter shape */
+  TFHE_ERR_CUDA = -2,    /* CUDA runtime failure or no usable device   */
+  TFHE_ERR_STATE = -3,   /* e.g. cloud key not loaded                  */
+  TFHE_ERR_NOMEM = -4
+} tfhe_status;
+
+/* Gate opcodes for tfhe_gate_batch.  Linear prologue c = sa*a + sb*b + (0,..,0,bias), then one
+ * bootstrap with the default test vector.  evaluator/gates_helper.go:10-63 (NAND, AND, OR, XOR),
+ * gates/gates.go:52-104 (XNOR, NOR, ANDNY, ANDYN, ORNY, ORYN), gates/gates.go:107-114 (MUX =
+ * OR(AND(a,b), AND(NOT a, c)), three bootstraps), gates/gates.go:117-130 (NOT, COPY: no bootstrap). */
+typedef enum {
+  TFHE_OP_NAND = 0, TFHE_OP_AND = 1, TFHE_OP_OR = 2, TFHE_OP_XOR = 3, TFHE_OP_XNOR = 4,
+  TFHE_OP_NOR = 5, TFHE_OP_ANDNY = 6, TFHE_OP_ANDYN = 7, TFHE_OP_ORNY = 8, TFHE_OP_ORYN = 9,
+  TFHE_OP_MUX = 10, TFHE_OP_NOT = 11, TFHE_OP_COPY = 12
+} tfhe_op;
+
+/* --- lifecycle ------------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device` (>= 0).  Replaces evaluator.NewEvaluator
+ * (evaluator/evaluator.go:27-35) and the package-global evaluator of gates/gates.go:19-23. */
+int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out);
+void tfhe_ctx_destroy(tfhe_ctx* ctx);
+/* Message of the last failure on `ctx` (or of the last failed tfhe_ctx_create if ctx == NULL). */
+const char* tfhe_last_error(const tfhe_ctx* ctx);
+
+/* Uploads a cloudkey.CloudKey (cloudkey/cloudkey.go:16-21).  bsk_fft is taken in the reference's
+ * own Fourier layout and repacked on the device (scaled by 2/N, an exact power of two) into the
+ * engine's layout; ksk rows are re-strided for 16-byte loads; ksk may be NULL if only
+ * tfhe_blind_rotate_batch is used (cloudkey.NewCloudKeyNoKSK, cloudkey.go:34-57). */
+int tfhe_ctx_load_cloudkey(tfhe_ctx* ctx, uint32_t decomposition_offset, const double* bsk_fft,
+                           const uint32_t* ksk, const uint32_t* testvec);
+/* Same, from buffers already in this device's memory (e.g. filled by one NCCL broadcast from
+ * rank 0).  `stream` is a cudaStream_t (0 = default stream); returns after the repack is done. */
+int tfhe_ctx_load_cloudkey_device(tfhe_ctx* ctx, uint32_t decomposition_offset, const double* d_bsk_fft,
+                                  const uint32_t* d_ksk, const uint32_t* d_testvec, void* stream);
+
+/* --- the hot path, host buffers --------------------------------------------------------------- */
+
+/* count independent bootstraps: blind rotate -> sample extract(0) -> identity key switch.
+ * Replaces Evaluator.BootstrapAssign (evaluator/evaluator.go:139-148) and, with luts != NULL,
+ * Evaluator.BootstrapLUTAssign (evaluator/programmable_bootstrap.go:93-115), applied to every
+ * element.  luts: NULL => CloudKey.BlindRotateTestvec for all; else nluts in {1, count} TRLWE
+ * test vectors [nluts][2][N] (lut.LookUpTable.Poly). */
+int tfhe_bootstrap_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* ct_in, const uint32_t* luts,
+                         int64_t nluts, uint32_t* ct_out);
+
+/* count gates.  Replaces gates.{NAND..ORYN,MUX,NOT,Copy} (gates/gates.go:26-130) and
+ * gates.Batch{NAND,AND,OR,XOR,NOR,XNOR} (gates/gates.go:156-312; every element equals the
+ * single-gate path, and XNOR uses the single-gate bias, see SURVEY.md section 2 defects 1-2).
+ * ops: nops in {1, count} opcodes.  c is read only by TFHE_OP_MUX gates and may be NULL otherwise;
+ * b is ignored by NOT / COPY. */
+int tfhe_gate_batch(tfhe_ctx* ctx, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* a,
+                    const uint32_t* b, const uint32_t* c, uint32_t* out);
+
+/* Blind rotation only; output TRLWE [count][2][N].  Replaces Evaluator.BlindRotateAssign
+ * (evaluator/evaluator.go:110-135), trgsw.BlindRotate / trgsw.BatchBlindRotate
+ * (trgsw/trgsw.go:197-252). */
+int tfhe_blind_rotate_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* ct_in, const uint32_t* luts,
+                            int64_t nluts, uint32_t* trlwe_out);
+
+/* CMUX with bootstrapping-key row `bsk_index`: out = ct0 + BK[bsk_index] (x) (ct1 - ct0).
+ * Replaces Evaluator.CMuxAssign / ExternalProductAssign (evaluator/evaluator.go:50-106),
+ * trgsw.CMUX / ExternalProductWithFFT (trgsw/trgsw.go:108-194).  ct0 == NULL means ct0 = 0, i.e.
+ * the plain external product of ct1.  TRLWE batches [count][2][N]. */
+int tfhe_cmux_batch(tfhe_ctx* ctx, int64_t count, int32_t bsk_index, const uint32_t* ct0,
+                    const uint32_t* ct1, uint32_t* out);
+
+/* Sample extract at index 0 (trlwe/trlwe_ops.go:10-21): TRLWE [count][2][N] -> LWE [count][N+1]. */
+int tfhe_sample_extract_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* trlwe_in, uint32_t* lwe_out);
+
+/* Identity key switch N -> n (trgsw/keyswitch.go:10-37, trgsw/trgsw.go:285-311):
+ * LWE [count][N+1] -> LWE [count][n+1]. */
+int tfhe_key_switch_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* lwe_in, uint32_t* ct_out);
+
+/* --- the hot path, device buffers (inputs already resident in HBM) -------------------------- */
+/* Same semantics; pointers are device pointers on the context's device; work is enqueued on
+ * `stream` (cudaStream_t, 0 = default) and NOT synchronised. */
+int tfhe_bootstrap_batch_device(tfhe_ctx* ctx, int64_t count, const uint32_t* d_ct_in, const uint32_t* d_luts,
+                                int64_t nluts, uint32_t* d_ct_out, void* stream);
+int tfhe_gate_batch_device(tfhe_ctx* ctx, int64_t count, const uint8_t* d_ops, int64_t nops, const uint32_t* d_a,
+                           const uint32_t* d_b, const uint32_t* d_c, uint32_t* d_out, void* stream);
+
+/* --- introspection ---------------------------------------------------------------------------- */
+/* Number of CUDA kernels this context has launched since creation (bench.py: gpu_launches). */
+int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
+/* Per-stage device timing for bench.py's roofline: when enabled, every bootstrap batch records CUDA events on
+ * its launching stream around the blind-rotate kernel and the key-switch kernel.  tfhe_ctx_collect_timing waits
+ * for the recorded events and returns {blind_rotate_ms_total, blind_rotate_launches, key_switch_ms_total,
+ * key_switch_launches} since the previous collect. */
+int tfhe_ctx_set_timing(tfhe_ctx* ctx, int enable);
+int tfhe_ctx_collect_timing(tfhe_ctx* ctx, double out[4]);
+/* Algorithmic bytes per bootstrap of SURVEY.md section 8(d): n*2L*2*N*8 + N*t*(1-1/base)*(n+1)*4 + io. */
+int64_t tfhe_ctx_algorithmic_bytes_per_bootstrap(const tfhe_ctx* ctx);
+/* Library version string. */
+const char* tfhe_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFHE_B200_H */

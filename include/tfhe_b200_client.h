@@ -1,0 +1,37 @@
+/*
+ * tfhe_b200_client.h — host-side client helpers (libtfhe_b200_client.so, plain C++, no CUDA).
+ *
+ * NOT part of the drop-in boundary: in an integration with the reference these operations stay
+ * in its own Go packages (key/key.go, tlwe/tlwe.go, tlwe/programmable_encrypt.go,
+ * cloudkey/cloudkey.go, lut/generator.go).  They exist here so that bench.py, the examples and the
+ * host-side mirror can make valid keys and ciphertexts on a machine without a Go toolchain.
+ * Layouts are those of tfhe_b200.h.
+ */
+#ifndef TFHE_B200_CLIENT_H
+#define TFHE_B200_CLIENT_H
+#include "tfhe_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* key.NewSecretKey, key/key.go:16-45 */
+void tfhe_client_secret_key(const tfhe_params* P, uint64_t seed, uint32_t* key_lv0, uint32_t* key_lv1);
+/* tlwe.EncryptBool / DecryptBool, tlwe/tlwe.go:54-74 */
+void tfhe_client_encrypt_bool(const tfhe_params* P, double alpha, const uint32_t* key_lv0, uint64_t seed,
+                              int64_t count, const uint8_t* bits, uint32_t* out);
+void tfhe_client_decrypt_bool(const tfhe_params* P, const uint32_t* key_lv0, int64_t count, const uint32_t* ct,
+                              uint8_t* bits);
+/* tlwe.EncryptLWEMessage / DecryptLWEMessage, tlwe/programmable_encrypt.go:12-54 */
+void tfhe_client_encrypt_message(const tfhe_params* P, double alpha, const uint32_t* key_lv0, uint64_t seed,
+                                 int64_t count, const int32_t* msgs, int32_t modulus, uint32_t* out);
+void tfhe_client_decrypt_message(const tfhe_params* P, const uint32_t* key_lv0, int64_t count, const uint32_t* ct,
+                                 int32_t modulus, int32_t* msgs);
+/* lut.Generator.GenLookUpTable, lut/generator.go:49-100; fvals[x] = f(x); lut_out is a TRLWE [2][N] */
+void tfhe_client_gen_lut(const tfhe_params* P, int32_t modulus, const int32_t* fvals, uint32_t* lut_out);
+/* cloudkey.NewCloudKey, cloudkey/cloudkey.go:24-31,60-145 */
+void tfhe_client_cloud_key(const tfhe_params* P, double alpha_lv0, double alpha_lv1, const uint32_t* key_lv0,
+                           const uint32_t* key_lv1, uint64_t seed, int threads, uint32_t* decomposition_offset,
+                           uint32_t* testvec, uint32_t* ksk, double* bsk_fft);
+#ifdef __cplusplus
+}
+#endif
+#endif
