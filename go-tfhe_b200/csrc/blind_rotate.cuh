@@ -20,6 +20,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Build-time tuning knobs (defaults are the measured best; see profiles/).
+#ifndef TFHE_BR_UNROLL_POLY
+#define TFHE_BR_UNROLL_POLY 2   // 2 = fully unrolled over the A/B polynomials, 1 = rolled
+#endif
+#ifndef TFHE_BR_UNROLL_LVL
+#define TFHE_BR_UNROLL_LVL 8    // >= L = fully unrolled over decomposition levels, 1 = rolled
+#endif
+#ifndef TFHE_BR_KEEP_OWN
+#define TFHE_BR_KEEP_OWN 0      // 1: exchanges keep the one point that does not change owner in its register (measured 3.5% slower: the predicated asm blocks pin the schedule)
+#endif
+#define TFHE_PRAGMA_(x) _Pragma(#x)
+#define TFHE_UNROLL(n) TFHE_PRAGMA_(unroll n)
+
 namespace tfhe {
 
 struct Tw4 { double2 s[4]; };  // twiddles of one radix-8 block: S(m,i), S(2m,2i), S(4m,4i), S(4m,4i+2)
@@ -30,6 +43,7 @@ struct BrArgs {
   const uint32_t* luts;     // NULL or [nluts][2][N]
   long long nluts;
   const double2* bsk;       // [n][2L][2][8][T], pre-scaled by 1/M
+  cudaTextureObject_t bsk_tex;  // the same buffer as a linear uint4 texture (TEX-path variant)
   const double2* tw_tab;    // per-pass twiddle tables for passes >= 1 (4 double2 per block)
   uint32_t* out;            // out_mode 0: TRLWE [count][2][N]; 1: extracted LWE [count][N+1]
   int n;
@@ -139,12 +153,62 @@ struct Geo {
   __device__ __forceinline__ static int block_of(int k, int tau) { return tau / stride(k); }
 };
 
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// predicated 16-byte shared-memory load: v keeps its value where pred is false (no divergent branch)
+__device__ __forceinline__ void lds_if(double2& v, const double2* p, bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
+      : "+d"(v.x), "+d"(v.y)
+      : "r"(smem_u32(p)), "r"((int)pred)
+      : "memory");
+}
+
+__device__ __forceinline__ void sts_if(double2* p, const double2& v, bool pred) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(smem_u32(p)),
+               "d"(v.x), "d"(v.y), "r"((int)pred)
+               : "memory");
+}
+
 // 16-byte-slot swizzle: conflict-free for every pass stride used above.
 __device__ __forceinline__ int swz(int p) { return p ^ ((p >> 3) & 7); }
 
-template <int LOGM>
+// SINGLE = false: two exchange buffers used alternately (one block barrier per exchange).
+// SINGLE = true : one exchange buffer; the write-after-read hazard is covered by an mbarrier on which every thread
+//                 arrives (non-blocking) after its reads and waits before its next writes (normally long complete).
+template <int LOGM, bool SINGLE = false>
 struct Fft {
   using G = Geo<LOGM>;
+  uint64_t* rd_bar = nullptr;
+  uint32_t rd_phase = 0;
   // Per-thread persistent state: twiddles of the last pass (unique per thread) and the ping-pong
   // parity of the exchange buffers.
   double2 tl0, tl1, tl2, tl3;
@@ -153,6 +217,11 @@ struct Fft {
   const Tw4* tab;         // twiddle tables for passes >= 1
   int tau;
 
+  // call from every thread, before a __syncthreads(); rd_bar_ must have been mbar_init'ed with count T
+  __device__ __forceinline__ void init_single(uint64_t* rd_bar_) {
+    rd_bar = rd_bar_;
+    rd_phase = 0;
+  }
   __device__ __forceinline__ void init(double2* ex_, const double2* tw_tab, int tau_) {
     ex = ex_;
     tab = reinterpret_cast<const Tw4*>(tw_tab);
@@ -162,17 +231,40 @@ struct Fft {
     tl0 = e->s[0]; tl1 = e->s[1]; tl2 = e->s[2]; tl3 = e->s[3];
   }
 
-  template <int KW, int KR>
-  __device__ __forceinline__ void exchange(double2 (&x)[8]) {
-    double2* buf = ex + (parity ? G::M : 0);
-    parity ^= 1;
+  struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+  // hook() runs right after the block barrier (every thread has finished whatever preceded this exchange)
+  template <int KW, int KR, class Hook>
+  __device__ __forceinline__ void exchange(double2 (&x)[8], const Hook& hook) {
+    double2* buf = ex;
+    if constexpr (SINGLE) {
+      mbar_wait(rd_bar, rd_phase);  // every thread has finished reading the previous exchange
+      rd_phase ^= 1u;
+    } else {
+      buf += (parity ? G::M : 0);
+      parity ^= 1;
+    }
     const int wb = G::base(KW, tau), rb = G::base(KR, tau);
+    // Between two full passes exactly one of a thread's 8 points keeps both its owner and its register slot
+    // (slot (tau / finer stride) % 8): it stays in its register, skipping 1/8 of the shared-memory traffic.
+    constexpr bool KEEP = TFHE_BR_KEEP_OWN && (KW < G::NFULL) && (KR < G::NFULL);
+    const int own = KEEP ? ((tau / G::stride(KW > KR ? KW : KR)) & 7) : -1;
 #pragma unroll
-    for (int a = 0; a < 8; a++) buf[swz(wb + G::stride(KW) * a)] = x[a];
+    for (int a = 0; a < 8; a++) {
+      if constexpr (KEEP) sts_if(buf + swz(wb + G::stride(KW) * a), x[a], a != own);
+      else buf[swz(wb + G::stride(KW) * a)] = x[a];
+    }
     __syncthreads();
+    hook();
 #pragma unroll
-    for (int a = 0; a < 8; a++) x[a] = buf[swz(rb + G::stride(KR) * a)];
+    for (int a = 0; a < 8; a++) {
+      if constexpr (KEEP) lds_if(x[a], buf + swz(rb + G::stride(KR) * a), a != own);  // predicated, never a branch
+      else x[a] = buf[swz(rb + G::stride(KR) * a)];
+    }
+    if constexpr (SINGLE) mbar_arrive(rd_bar);
   }
+  template <int KW, int KR>
+  __device__ __forceinline__ void exchange(double2 (&x)[8]) { exchange<KW, KR>(x, NoHook()); }
 
   template <int K>
   __device__ __forceinline__ void fwd_pass(double2 (&x)[8], const Tw4& tw0) {
@@ -200,19 +292,30 @@ struct Fft {
   }
 
   // in: x[a] = z[tau + T a] (folded coefficients); out: x[e] = spectrum at position 8 tau + e
-  __device__ __forceinline__ void forward(double2 (&x)[8], const Tw4& tw0) {
+  template <class Hook>
+  __device__ __forceinline__ void forward(double2 (&x)[8], const Tw4& tw0, const Hook& hook) {
     fwd_pass<0>(x, tw0);
-    if constexpr (G::NPASS > 1) { exchange<0, 1>(x); fwd_pass<1>(x, tw0); }
+    if constexpr (G::NPASS > 1) { exchange<0, 1>(x, hook); fwd_pass<1>(x, tw0); }
     if constexpr (G::NPASS > 2) { exchange<1, 2>(x); fwd_pass<2>(x, tw0); }
     if constexpr (G::NPASS > 3) { exchange<2, 3>(x); fwd_pass<3>(x, tw0); }
   }
-  // exact inverse of forward() up to the factor M (folded into the bootstrapping key)
-  __device__ __forceinline__ void inverse(double2 (&x)[8], const Tw4& tw0) {
-    if constexpr (G::NPASS > 3) { inv_pass<3>(x, tw0); exchange<3, 2>(x); }
-    if constexpr (G::NPASS > 2) { inv_pass<2>(x, tw0); exchange<2, 1>(x); }
-    if constexpr (G::NPASS > 1) { inv_pass<1>(x, tw0); exchange<1, 0>(x); }
+  __device__ __forceinline__ void forward(double2 (&x)[8], const Tw4& tw0) { forward(x, tw0, NoHook()); }
+  // exact inverse of forward() up to the factor M (folded into the bootstrapping key); hook after the FIRST barrier
+  template <class Hook>
+  __device__ __forceinline__ void inverse(double2 (&x)[8], const Tw4& tw0, const Hook& hook) {
+    if constexpr (G::NPASS > 3) {
+      inv_pass<3>(x, tw0); exchange<3, 2>(x, hook);
+      inv_pass<2>(x, tw0); exchange<2, 1>(x);
+      inv_pass<1>(x, tw0); exchange<1, 0>(x);
+    } else if constexpr (G::NPASS > 2) {
+      inv_pass<2>(x, tw0); exchange<2, 1>(x, hook);
+      inv_pass<1>(x, tw0); exchange<1, 0>(x);
+    } else if constexpr (G::NPASS > 1) {
+      inv_pass<1>(x, tw0); exchange<1, 0>(x, hook);
+    }
     inv_pass<0>(x, tw0);
   }
+  __device__ __forceinline__ void inverse(double2 (&x)[8], const Tw4& tw0) { inverse(x, tw0, NoHook()); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -247,8 +350,22 @@ __device__ __forceinline__ uint32_t rot_read(const uint32_t* P, int idx) {
 // ---------------------------------------------------------------------------------------------
 // One CMUX step on the shared-memory accumulator: acc += BK (x) (X^at * acc - acc).
 // ---------------------------------------------------------------------------------------------
-template <int LOGN, int L, int BGBIT, bool SMALL>
-__device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1>& fft, const double2* __restrict__ bk,
+// key-row fetch policies for the MAC: straight LDG (LSU pipe) or texture fetch (TEX pipe)
+struct KeyLdg {
+  const double2* __restrict__ p;
+  __device__ __forceinline__ double2 operator()(int idx) const { return __ldg(p + idx); }
+};
+struct KeyTex {
+  cudaTextureObject_t tex;
+  int base;  // in double2 units
+  __device__ __forceinline__ double2 operator()(int idx) const {
+    const uint4 v = tex1Dfetch<uint4>(tex, base + idx);
+    return make_double2(__hiloint2double((int)v.y, (int)v.x), __hiloint2double((int)v.w, (int)v.z));
+  }
+};
+
+template <int LOGN, int L, int BGBIT, bool SMALL, class Key>
+__device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, false>& fft, const Key bk,
                                                  int at, uint32_t offset, const Tw4& tw0) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
   constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
@@ -257,7 +374,7 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1>& f
 #pragma unroll
   for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
 
-#pragma unroll
+  TFHE_UNROLL(TFHE_BR_UNROLL_POLY)
   for (int poly = 0; poly < 2; poly++) {
     const uint32_t* P = acc + poly * N;
     uint32_t dre[8], dim[8];
@@ -268,7 +385,7 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1>& f
       dre[a] = rot_read<N>(P, ib + T * a) - P[j] + offset;
       dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + offset;
     }
-#pragma unroll
+    TFHE_UNROLL(TFHE_BR_UNROLL_LVL)
     for (int lvl = 0; lvl < L; lvl++) {
       double2 x[8];
       constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
@@ -279,12 +396,12 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1>& f
         x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
       }
       fft.forward(x, tw0);
-      const double2* __restrict__ rowA = bk + ((poly * L + lvl) * 2 + 0) * M + tau;
-      const double2* __restrict__ rowB = rowA + M;
+      const int rowA = ((poly * L + lvl) * 2 + 0) * M + tau;
+      const int rowB = rowA + M;
 #pragma unroll
       for (int e = 0; e < 8; e++) {
-        const double2 ka = __ldg(rowA + e * T);
-        const double2 kb = __ldg(rowB + e * T);
+        const double2 ka = bk(rowA + e * T);
+        const double2 kb = bk(rowB + e * T);
         accA[e].x = fma(x[e].x, ka.x, accA[e].x);
         accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
         accA[e].y = fma(x[e].x, ka.y, accA[e].y);
@@ -321,10 +438,10 @@ constexpr size_t br_smem_bytes(int n) {
 // ---------------------------------------------------------------------------------------------
 // The kernel: grid = count gates, block = T = N/16 threads.
 // ---------------------------------------------------------------------------------------------
-template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
+template <int LOGN, int L, int BGBIT, bool SMALL, int MINB, bool TEX = false>
 __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_kernel(const BrArgs A) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][M]
   unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 32 * M);
@@ -354,7 +471,10 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_kernel(c
   for (int i = 0; i < n; i++) {
     const int at = abar[i];
     if (at == 0) continue;  // X^0: ct1 - ct0 = 0, digits are all zero, the step is an exact no-op
-    cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, A.bsk + row_stride * i, at, A.offset, A.tw0);
+    if constexpr (TEX)
+      cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyTex{A.bsk_tex, (int)(row_stride * i)}, at, A.offset, A.tw0);
+    else
+      cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyLdg{A.bsk + row_stride * i}, at, A.offset, A.tw0);
     __syncthreads();
   }
 
@@ -368,11 +488,160 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_kernel(c
   }
 }
 
+// =============================================================================================
+// TMA-staged variant: the bootstrapping-key row-set of the current (step, digit) is brought into shared memory by
+// one bulk asynchronous copy (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) issued by one thread a
+// transform ahead of its use, so the MAC reads the key with short-latency LDS and the L2 latency is hidden
+// without spending registers on prefetch.  One 2*M*16-byte buffer (16 KiB at N=1024) is recycled per digit:
+// the copy for digit r is issued right after the first block barrier that follows the MAC of digit r-1.
+// =============================================================================================
+template <int LOGN>
+constexpr size_t br_staged_smem_bytes(int n) {
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)(1 << (LOGN - 1)) * 16 /*exchange (single)*/ +
+         (size_t)2 * 2 * (1 << (LOGN - 1)) * 16 /*2 key-row buffers (A,B spectra)*/ +
+         (size_t)(((n + 1) * 4 + 15) / 16 * 16) /*abar+steps*/ + 32 /*mbarriers*/;
+}
+
+template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
+__global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_staged_kernel(const BrArgs A) {
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  constexpr uint32_t ROW_BYTES = 2u * M * 16u;           // one digit: A spectrum then B spectrum
+  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                         // [2][N]
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);                    // [M]
+  double2* kbuf = reinterpret_cast<double2*>(smem_raw + 8 * N + 16 * M);         // [2 buffers][2][8][T]
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * M + 64 * M);
+  const int tau = threadIdx.x;
+  const long long g = blockIdx.x;
+  const int n = A.n;
+  unsigned short* steps = abar + n;                                              // indices of the non-trivial steps
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + 8 * N + 16 * M + 64 * M + (((n + 1) * 4 + 15) / 16 * 16));
+  uint64_t* full = mbar;        // [2]: key-row buffer b has landed
+  uint64_t* rd_bar = mbar + 2;  // exchange-buffer reads done
+  __shared__ int s_nsteps;
+  const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+
+  for (int i = tau; i < n; i += T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
+  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
+  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
+  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+  for (int j = tau; j < N; j += T) {
+    const int idx = (j - btil) & (2 * N - 1);
+    const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
+    acc[j] = (idx & N) ? ~va : va;
+    acc[N + j] = (idx & N) ? ~vb : vb;
+  }
+  if (tau == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(rd_bar, T);
+  }
+  Fft<LOGN - 1, true> fft;
+  fft.init(ex, A.tw_tab, tau);
+  fft.init_single(rd_bar);
+  __syncthreads();
+  mbar_arrive(rd_bar);  // completes phase 0: "no reads outstanding" before the first exchange
+  if (tau == 0) {  // X^0 steps are exact no-ops (digits all zero): drop them from the schedule
+    int c = 0;
+    for (int i = 0; i < n; i++)
+      if (abar[i] != 0) steps[c++] = (unsigned short)i;
+    s_nsteps = c;
+  }
+  __syncthreads();
+  const int nsteps = s_nsteps;
+  const int njobs = nsteps * 2 * L;                 // job q = (schedule entry q / 2L, digit q % 2L), buffer q & 1
+  const size_t row_stride = (size_t)2 * L * 2 * M;  // double2 per step
+  const char* bsk_bytes = reinterpret_cast<const char*>(A.bsk);
+  auto issue = [&](int q) {  // thread 0 only
+    const int k = q / (2 * L), r = q - k * (2 * L);
+    uint64_t* fb = &full[q & 1];
+    mbar_arrive_expect_tx(fb, ROW_BYTES);
+    bulk_copy_g2s(kbuf + (size_t)(q & 1) * 2 * M,
+                  bsk_bytes + ((size_t)steps[k] * row_stride + (size_t)r * 2 * M) * sizeof(double2), ROW_BYTES, fb);
+  };
+  if (tau == 0 && njobs > 0) issue(0);
+  int q = 0;
+
+  for (int k = 0; k < nsteps; k++) {
+    const int at = abar[steps[k]];
+    double2 accA[8], accB[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
+    TFHE_UNROLL(TFHE_BR_UNROLL_POLY)
+    for (int poly = 0; poly < 2; poly++) {
+      const uint32_t* P = acc + poly * N;
+      uint32_t dre[8], dim[8];
+      const int ib = (tau - at) & (2 * N - 1);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        dre[a] = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
+        dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
+      }
+      TFHE_UNROLL(TFHE_BR_UNROLL_LVL)
+      for (int lvl = 0; lvl < L; lvl++, q++) {
+        double2 x[8];
+        constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+        const int sh = 32 - (lvl + 1) * BGBIT;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+          x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
+          x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+        }
+        // The block barrier inside the first exchange proves every thread has finished the MAC of job q-1, whose
+        // buffer ((q+1) & 1) is therefore free: stage job q+1 into it, one whole transform ahead of its use.
+        fft.forward(x, A.tw0, [&]() { if (tau == 0 && q + 1 < njobs) issue(q + 1); });
+        mbar_wait(&full[q & 1], (uint32_t)(q >> 1) & 1u);
+        const double2* rowA = kbuf + (size_t)(q & 1) * 2 * M + tau;
+        const double2* rowB = rowA + M;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const double2 ka = rowA[e * T];
+          const double2 kb = rowB[e * T];
+          accA[e].x = fma(x[e].x, ka.x, accA[e].x);
+          accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
+          accA[e].y = fma(x[e].x, ka.y, accA[e].y);
+          accA[e].y = fma(x[e].y, ka.x, accA[e].y);
+          accB[e].x = fma(x[e].x, kb.x, accB[e].x);
+          accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
+          accB[e].y = fma(x[e].x, kb.y, accB[e].y);
+          accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+        }
+      }
+    }
+    fft.inverse(accA, A.tw0);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      acc[j] += to_torus<SMALL>(accA[a].x);
+      acc[j + M] += to_torus<SMALL>(accA[a].y);
+    }
+    fft.inverse(accB, A.tw0);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      acc[N + j] += to_torus<SMALL>(accB[a].x);
+      acc[N + j + M] += to_torus<SMALL>(accB[a].y);
+    }
+    __syncthreads();
+  }
+
+  if (A.out_mode == 0) {
+    uint32_t* o = A.out + g * (2 * N);
+    for (int j = tau; j < 2 * N; j += T) o[j] = acc[j];
+  } else {
+    uint32_t* o = A.out + g * (N + 1);
+    for (int j = tau; j < N; j += T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
+    if (tau == 0) o[N] = acc[N];
+  }
+}
+
 // Single CMUX / external product on global-memory TRLWEs (parity-test granularity; rows a9, a14).
 template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
 __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const CmuxArgs A) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);       // holds ct0, becomes the result
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);
   uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 32 * M);  // [2][N]

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -64,6 +65,10 @@ struct tfhe_ctx {
   int sm_count = 0;
   std::string err;
   // optional per-stage timing (tfhe_ctx_set_timing): CUDA events on the launching stream
+  // how blind rotate reads the key rows: 0 = LDG straight from L2 (default, fastest measured), 1 = TMA-staged through
+  // shared memory (cp.async.bulk + mbarrier), 2 = texture fetches.  See profiles/ for the measurements behind the default.
+  int br_variant = 0;
+  cudaTextureObject_t bsk_tex = 0;
   bool timing = false;
   struct StageEv { cudaEvent_t e0, e1, e2; };
   std::vector<StageEv> ev_live, ev_free;
@@ -123,20 +128,32 @@ void build_twiddles(Tw4& tw0, std::vector<Tw4>& tab) {
 struct Variant {
   int logN, L, bgbit;
   bool small;
-  void (*br)(const BrArgs);
+  void (*br)(const BrArgs);          // key rows read straight from L2 (LDG)
+  void (*br_tex)(const BrArgs);      // key rows fetched through the texture pipe
+  void (*br_staged)(const BrArgs);   // key rows TMA-staged into shared memory (cp.async.bulk + mbarrier)
   void (*cmux)(const CmuxArgs);
   size_t (*br_smem)(int n);
+  size_t (*br_staged_smem)(int n);
 };
 template <int LOGN> size_t br_smem(int n) { return br_smem_bytes<LOGN>(n); }
-#define VARIANT(LOGN, L, BG, SMALL, MINB)                                                         \
-  { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>, cmux_kernel<LOGN, L, BG, SMALL, MINB>, \
-    br_smem<LOGN> }
+template <int LOGN> size_t br_staged_smem(int n) { return br_staged_smem_bytes<LOGN>(n); }
+#ifndef TFHE_BR_STAGED_MINB_N1024
+#define TFHE_BR_STAGED_MINB_N1024 4
+#endif
+#define VARIANT(LOGN, L, BG, SMALL, MINB, MINBS)                                                    \
+  { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>,                              \
+    blind_rotate_kernel<LOGN, L, BG, SMALL, MINB, true>,                                            \
+    blind_rotate_staged_kernel<LOGN, L, BG, SMALL, MINBS>, cmux_kernel<LOGN, L, BG, SMALL, MINB>,   \
+    br_smem<LOGN>, br_staged_smem<LOGN> }
+#ifndef TFHE_BR_MINB_N1024
+#define TFHE_BR_MINB_N1024 4
+#endif
 const Variant kVariants[] = {
-    VARIANT(10, 3, 6, true, 4),    // 80 / 110 / 128-bit  (params/params.go:83-180)
-    VARIANT(10, 2, 10, false, 4),  // Uint1               (params.go:194-223)
-    VARIANT(9, 1, 18, false, 8),   // Uint2               (params.go:236-265)
-    VARIANT(10, 1, 23, false, 4),  // Uint3               (params.go:277-306)
-    VARIANT(11, 1, 22, false, 2),  // Uint4 / Uint5       (params.go:318-391)
+    VARIANT(10, 3, 6, true, TFHE_BR_MINB_N1024, TFHE_BR_STAGED_MINB_N1024),  // 80 / 110 / 128-bit (params/params.go:83-180)
+    VARIANT(10, 2, 10, false, 4, 4),  // Uint1               (params.go:194-223)
+    VARIANT(9, 1, 18, false, 8, 8),   // Uint2               (params.go:236-265)
+    VARIANT(10, 1, 23, false, 4, 4),  // Uint3               (params.go:277-306)
+    VARIANT(11, 1, 22, false, 2, 2),  // Uint4 / Uint5       (params.go:318-391)
 };
 
 int find_variant(const tfhe_params& P) {
@@ -164,7 +181,10 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   a.ct_in = d_ct; a.testvec = c->d_testvec; a.luts = d_luts; a.nluts = nluts; a.bsk = c->d_bsk; a.tw_tab = c->d_tw;
   a.out = d_out; a.n = c->P.n; a.offset = c->offset; a.out_mode = out_mode; a.tw0 = c->tw0;
   const int T = c->P.N / 16;
-  V.br<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  a.bsk_tex = c->bsk_tex;
+  if (c->br_variant == 1) V.br_staged<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
+  else if (c->br_variant == 2) V.br_tex<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  else V.br<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   c->launches++;
   CK(c, cudaGetLastError());
   return 0;
@@ -173,6 +193,7 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
 int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s) {
   if (count == 0) return 0;
   const size_t sm = (size_t)c->P.N * c->P.iks_t * sizeof(uint32_t);
+  if (sm > 128 * 1024) return fail(c, TFHE_ERR_ARG, "N * iks_t too large for the key-switch kernel");
   key_switch_kernel<<<(unsigned)count, 256, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
                                                      c->P.iks_t, c->ksk_stride);
   c->launches++;
@@ -264,12 +285,19 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
   const Variant& V = kVariants[v];
-  if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(P.n))) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)  // limit, not allocation: n <= 4096
     return bail("cudaFuncSetAttribute(blind_rotate)", e);
+  if ((e = cudaFuncSetAttribute(V.br_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_staged_smem(4096))) !=
+      cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_staged)", e);
+  if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
+  if (const char* sel = getenv("TFHE_B200_BR"))
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : 0;
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
   if ((e = cudaFuncSetAttribute(key_switch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((size_t)P.N * P.iks_t * 4))) != cudaSuccess)
+                                128 * 1024)) != cudaSuccess)  // a limit shared by every context of the process
     return bail("cudaFuncSetAttribute(key_switch)", e);
   *out = c;
   return TFHE_OK;
@@ -284,6 +312,7 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
     b->release();
   for (auto* v : {&c->ev_live, &c->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); cudaEventDestroy(ev.e2); }
+  if (c->bsk_tex) cudaDestroyTextureObject(c->bsk_tex);
   if (c->d_bsk) cudaFree(c->d_bsk);
   if (c->d_ksk) cudaFree(c->d_ksk);
   if (c->d_testvec) cudaFree(c->d_testvec);
@@ -316,6 +345,17 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
     c->has_ksk = true;
   }
   CK(c, cudaStreamSynchronize(s));
+  if (!c->bsk_tex) {
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = c->d_bsk;
+    rd.res.linear.desc = cudaCreateChannelDesc<uint4>();
+    rd.res.linear.sizeInBytes = polys * M * sizeof(double2);
+    cudaTextureDesc td{};
+    td.readMode = cudaReadModeElementType;
+    if (cudaCreateTextureObject(&c->bsk_tex, &rd, &td, nullptr) != cudaSuccess) { c->bsk_tex = 0; cudaGetLastError(); }
+  }
+  if (c->br_variant == 2 && !c->bsk_tex) return fail(c, TFHE_ERR_CUDA, "texture object over the bootstrapping key failed");
   c->offset = offset;
   c->key_loaded = true;
   return TFHE_OK;
@@ -429,7 +469,6 @@ int tfhe_gate_batch_device(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64
   }
   if (nm) {  // level 2: OR(andAB, andNotAC)
     uint32_t* in2 = in1;  // reuse
-    uint8_t dummy = 0; (void)dummy;
     mux_or_prepare_kernel<<<(unsigned)nm, 256, 0, s>>>(nm, nullptr, 0, out1 + (size_t)nb * n1, out1 + (size_t)(nb + nm) * n1,
                                                        in2, c->P.n);
     c->launches++;
@@ -572,6 +611,14 @@ int tfhe_key_switch_batch(tfhe_ctx* c, int64_t count, const uint32_t* lwe_in, ui
 }
 
 int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) { return c ? c->launches : 0; }
+
+int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
+  if (!c) return TFHE_ERR_ARG;
+  if (variant < 0 || variant > 2) return fail(c, TFHE_ERR_ARG, "variant must be 0 (ldg), 1 (tma) or 2 (tex)");
+  if (variant == 2 && c->key_loaded && !c->bsk_tex) return fail(c, TFHE_ERR_STATE, "no texture object");
+  c->br_variant = variant;
+  return TFHE_OK;
+}
 
 int tfhe_ctx_set_timing(tfhe_ctx* c, int enable) {
   if (!c) return TFHE_ERR_ARG;

@@ -146,6 +146,11 @@ class Context:
         self._ck(self.lib.tfhe_gate_batch_device(self.h, count, _ptr(ov), len(ov), d_a, d_b, d_c, d_out, stream),
                  "tfhe_gate_batch_device")
 
+    def set_blind_rotate_variant(self, variant):
+        """'ldg' (default) | 'tma' | 'tex' — how key rows reach the MAC; results are identical."""
+        v = {"ldg": 0, "tma": 1, "tex": 2}[variant] if isinstance(variant, str) else int(variant)
+        self._ck(self.lib.tfhe_ctx_set_blind_rotate_variant(self.h, v), "tfhe_ctx_set_blind_rotate_variant")
+
     def set_timing(self, enable=True):
         self._ck(self.lib.tfhe_ctx_set_timing(self.h, 1 if enable else 0), "tfhe_ctx_set_timing")
 

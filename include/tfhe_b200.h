@@ -136,6 +136,10 @@ int tfhe_gate_batch_device(tfhe_ctx* ctx, int64_t count, const uint8_t* d_ops, i
 /* --- introspection ---------------------------------------------------------------------------- */
 /* Number of CUDA kernels this context has launched since creation (bench.py: gpu_launches). */
 int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
+/* Selects how the blind-rotate kernel reads bootstrapping-key rows: 0 = LDG straight from L2 (default),
+ * 1 = TMA-staged through shared memory (cp.async.bulk + mbarrier), 2 = texture-pipe fetches.  All three compute
+ * identical results; the default is the fastest measured (profiles/). */
+int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
 /* Per-stage device timing for bench.py's roofline: when enabled, every bootstrap batch records CUDA events on
  * its launching stream around the blind-rotate kernel and the key-switch kernel.  tfhe_ctx_collect_timing waits
  * for the recorded events and returns {blind_rotate_ms_total, blind_rotate_launches, key_switch_ms_total,
