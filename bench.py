@@ -191,29 +191,13 @@ def main():
     ctx = T.Context(P, local)
 
     # --- cloud key: generated once on rank 0 (host client library), uploaded, and broadcast over NCCL -----------
-    bsk_shape = (P.n, 2 * P.L, 2, P.N)
-    ksk_shape = (P.ksk_rows, n1)
     sk = T.key.NewSecretKey(P, 2024)           # deterministic: every rank derives the same secret key
-    if rank == 0:
-        ck = T.cloudkey.NewCloudKey(sk, 2025)
-        d_bsk = torch.from_numpy(ck.BootstrappingKey).to(dev)
-        d_ksk = torch.from_numpy(ck.KeySwitchingKey.view(np.int32)).to(dev)
-        d_tv = torch.from_numpy(ck.BlindRotateTestvec.view(np.int32)).to(dev)
-        offset = ck.DecompositionOffset
-        del ck
-    else:
-        d_bsk = torch.empty(bsk_shape, dtype=torch.float64, device=dev)
-        d_ksk = torch.empty(ksk_shape, dtype=torch.int32, device=dev)
-        d_tv = torch.empty((2, P.N), dtype=torch.int32, device=dev)
-        offset = 0
-    if world > 1:  # the one collective of the whole job: key broadcast at init over NVLink
-        dist.broadcast(d_bsk, 0); dist.broadcast(d_ksk, 0); dist.broadcast(d_tv, 0)
-        off_t = torch.tensor([offset], dtype=torch.int64, device=dev)
-        dist.broadcast(off_t, 0)
-        offset = int(off_t.item())
+    ck = T.cloudkey.NewCloudKey(sk, 2025) if rank == 0 else None
+    keys = T.sharding.broadcast_cloudkey(P, ck, dev, dist if world > 1 else None)  # the one collective of the job
+    del ck
     stream = torch.cuda.current_stream()
-    ctx.load_cloudkey_device(offset, d_bsk.data_ptr(), d_ksk.data_ptr(), d_tv.data_ptr(), stream.cuda_stream)
-    del d_bsk, d_ksk, d_tv
+    T.sharding.load_broadcast_key(ctx, keys, stream.cuda_stream)
+    del keys
     torch.cuda.empty_cache()
 
     # --- synthetic inputs: fresh encryptions of uniform bits, different per rank ----------------------------

@@ -1,0 +1,220 @@
+// Package tfheb200 is the thin cgo shim between go-tfhe's Go types and the B200 engine's C ABI
+// (include/tfhe_b200.h, libtfhe_b200.so).  It flattens the pointer-rich reference types
+// ([]*tlwe.TLWELv0, []*trgsw.TRGSWLv1FFT, ...) into contiguous buffers, makes ONE C call per batch,
+// and scatters the results into freshly allocated reference types, so gates.* / evaluator.* keep
+// their signatures.  Errors become panics, matching the reference's convention.
+//
+// NOTE: this image has no Go toolchain; the file is reviewed by reading and mirrored line for line by
+// go-tfhe_b200/{cloudkey,evaluator,gates}.py, which the tests exercise against the same C ABI.
+package tfheb200
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../go-tfhe_b200/lib -ltfhe_b200 -Wl,-rpath,${SRCDIR}/../../go-tfhe_b200/lib
+#include <stdlib.h>
+#include "tfhe_b200.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"runtime"
+	"sync"
+	"unsafe"
+
+	"github.com/thedonutfactory/go-tfhe/cloudkey"
+	"github.com/thedonutfactory/go-tfhe/params"
+	"github.com/thedonutfactory/go-tfhe/tlwe"
+	"github.com/thedonutfactory/go-tfhe/trlwe"
+)
+
+// Op mirrors tfhe_op.
+type Op uint8
+
+const (
+	NAND Op = iota
+	AND
+	OR
+	XOR
+	XNOR
+	NOR
+	ANDNY
+	ANDYN
+	ORNY
+	ORYN
+	MUX
+	NOT
+	COPY
+)
+
+// Engine owns one tfhe_ctx (one GPU) with a cloud key resident on the device.
+type Engine struct {
+	mu  sync.Mutex // one call at a time per context
+	ctx *C.tfhe_ctx
+	n   int // TLWELv0.N
+	bigN int // TRGSWLv1.N
+}
+
+var (
+	enginesMu sync.Mutex
+	engines   = map[*cloudkey.CloudKey]*Engine{}
+)
+
+// For returns (creating and uploading on first use) the engine bound to ck on GPU 0.
+// gates.* call this, so user code keeps passing *cloudkey.CloudKey exactly as before.
+func For(ck *cloudkey.CloudKey) *Engine {
+	enginesMu.Lock()
+	defer enginesMu.Unlock()
+	if e, ok := engines[ck]; ok {
+		return e
+	}
+	e := New(ck, 0)
+	engines[ck] = e
+	return e
+}
+
+// New flattens ck (cloudkey/cloudkey.go:16-21) and uploads it to `device`.
+func New(ck *cloudkey.CloudKey, device int) *Engine {
+	g, l0 := params.GetTRGSWLv1(), params.GetTLWELv0()
+	p := C.tfhe_params{n: C.int32_t(l0.N), N: C.int32_t(g.N), L: C.int32_t(g.L), bgbit: C.int32_t(g.BGBIT),
+		basebit: C.int32_t(g.BASEBIT), iks_t: C.int32_t(g.IKS_T)}
+	var ctx *C.tfhe_ctx
+	if rc := C.tfhe_ctx_create(&p, C.int(device), &ctx); rc != 0 {
+		panic("tfhe_ctx_create: " + C.GoString(C.tfhe_last_error(nil)))
+	}
+	e := &Engine{ctx: ctx, n: l0.N, bigN: g.N}
+	runtime.SetFinalizer(e, func(e *Engine) { C.tfhe_ctx_destroy(e.ctx) })
+
+	// BootstrappingKey []*TRGSWLv1FFT -> [n][2L][2][N] float64, reference FourierPoly layout untouched
+	bsk := make([]float64, 0, l0.N*2*g.L*2*g.N)
+	for _, row := range ck.BootstrappingKey {
+		for _, t := range row.TRLWEFFT {
+			bsk = append(bsk, t.A.Coeffs...)
+			bsk = append(bsk, t.B.Coeffs...)
+		}
+	}
+	// KeySwitchingKey []*TLWELv0 (index base*t*i + base*j + k) -> [N*t*base][n+1] uint32
+	ksk := make([]uint32, 0, len(ck.KeySwitchingKey)*(l0.N+1))
+	for _, row := range ck.KeySwitchingKey {
+		ksk = appendTorus(ksk, row.P)
+	}
+	tv := appendTorus(appendTorus(make([]uint32, 0, 2*g.N), ck.BlindRotateTestvec.A), ck.BlindRotateTestvec.B)
+	e.check(C.tfhe_ctx_load_cloudkey(ctx, C.uint32_t(ck.DecompositionOffset), (*C.double)(&bsk[0]),
+		(*C.uint32_t)(&ksk[0]), (*C.uint32_t)(&tv[0])), "tfhe_ctx_load_cloudkey")
+	return e
+}
+
+func appendTorus(dst []uint32, src []params.Torus) []uint32 {
+	// params.Torus is uint32 (params/params.go:27): same memory layout
+	return append(dst, unsafe.Slice((*uint32)(unsafe.Pointer(&src[0])), len(src))...)
+}
+
+func (e *Engine) check(rc C.int, what string) {
+	if rc != 0 {
+		panic(fmt.Sprintf("%s failed (%d): %s", what, int(rc), C.GoString(C.tfhe_last_error(e.ctx))))
+	}
+}
+
+func (e *Engine) flatten(cts []*tlwe.TLWELv0) []uint32 {
+	out := make([]uint32, 0, len(cts)*(e.n+1))
+	for _, c := range cts {
+		out = appendTorus(out, c.P)
+	}
+	return out
+}
+
+func (e *Engine) unflatten(buf []uint32, count int) []*tlwe.TLWELv0 {
+	res := make([]*tlwe.TLWELv0, count)
+	for i := range res {
+		c := tlwe.NewTLWELv0() // fresh allocation per result, as gates.bootstrap does (gates/gates.go:137)
+		for j := range c.P {
+			c.P[j] = params.Torus(buf[i*(e.n+1)+j])
+		}
+		res[i] = c
+	}
+	return res
+}
+
+// GateBatch: one opcode per gate (or a single opcode for all); c may be nil unless an op is MUX.
+// Replaces the bodies of gates.{NAND..ORYN,MUX} and gates.Batch* (gates/gates.go:26-312).
+func (e *Engine) GateBatch(ops []Op, a, b, c []*tlwe.TLWELv0) []*tlwe.TLWELv0 {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	count := len(a)
+	if count == 0 {
+		return nil
+	}
+	fa, out := e.flatten(a), make([]uint32, count*(e.n+1))
+	var pb, pc *C.uint32_t
+	var fb, fc []uint32
+	if b != nil {
+		fb = e.flatten(b)
+		pb = (*C.uint32_t)(&fb[0])
+	}
+	if c != nil {
+		fc = e.flatten(c)
+		pc = (*C.uint32_t)(&fc[0])
+	}
+	e.check(C.tfhe_gate_batch(e.ctx, C.int64_t(count), (*C.uint8_t)(unsafe.Pointer(&ops[0])), C.int64_t(len(ops)),
+		(*C.uint32_t)(&fa[0]), pb, pc, (*C.uint32_t)(&out[0])), "tfhe_gate_batch")
+	runtime.KeepAlive(fb)
+	runtime.KeepAlive(fc)
+	return e.unflatten(out, count)
+}
+
+// BootstrapBatch replaces Evaluator.BootstrapAssign / BootstrapLUTAssign applied element-wise
+// (evaluator/evaluator.go:139-148, evaluator/programmable_bootstrap.go:93-115).
+// luts: nil => CloudKey.BlindRotateTestvec; else one TRLWE per ciphertext or a single one.
+func (e *Engine) BootstrapBatch(cts []*tlwe.TLWELv0, luts []*trlwe.TRLWELv1) []*tlwe.TLWELv0 {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	count := len(cts)
+	if count == 0 {
+		return nil
+	}
+	in, out := e.flatten(cts), make([]uint32, count*(e.n+1))
+	var pl *C.uint32_t
+	var fl []uint32
+	if len(luts) > 0 {
+		for _, l := range luts {
+			fl = appendTorus(appendTorus(fl, l.A), l.B)
+		}
+		pl = (*C.uint32_t)(&fl[0])
+	}
+	e.check(C.tfhe_bootstrap_batch(e.ctx, C.int64_t(count), (*C.uint32_t)(&in[0]), pl, C.int64_t(len(luts)),
+		(*C.uint32_t)(&out[0])), "tfhe_bootstrap_batch")
+	runtime.KeepAlive(fl)
+	return e.unflatten(out, count)
+}
+
+// BlindRotateBatch replaces trgsw.BatchBlindRotate (trgsw/trgsw.go:234-252).
+func (e *Engine) BlindRotateBatch(cts []*tlwe.TLWELv0, luts []*trlwe.TRLWELv1) []*trlwe.TRLWELv1 {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	count := len(cts)
+	if count == 0 {
+		return nil
+	}
+	in, out := e.flatten(cts), make([]uint32, count*2*e.bigN)
+	var pl *C.uint32_t
+	var fl []uint32
+	if len(luts) > 0 {
+		for _, l := range luts {
+			fl = appendTorus(appendTorus(fl, l.A), l.B)
+		}
+		pl = (*C.uint32_t)(&fl[0])
+	}
+	e.check(C.tfhe_blind_rotate_batch(e.ctx, C.int64_t(count), (*C.uint32_t)(&in[0]), pl, C.int64_t(len(luts)),
+		(*C.uint32_t)(&out[0])), "tfhe_blind_rotate_batch")
+	runtime.KeepAlive(fl)
+	res := make([]*trlwe.TRLWELv1, count)
+	for i := range res {
+		t := trlwe.NewTRLWELv1()
+		for j := 0; j < e.bigN; j++ {
+			t.A[j] = params.Torus(out[i*2*e.bigN+j])
+			t.B[j] = params.Torus(out[i*2*e.bigN+e.bigN+j])
+		}
+		res[i] = t
+	}
+	return res
+}
