@@ -8,6 +8,11 @@ ENGINE_PATH = os.environ.get("TFHE_B200_LIB") or os.path.join(HERE, "lib", "libt
 CLIENT_PATH = os.path.join(HERE, "lib", "libtfhe_b200_client.so")
 
 
+class GateDesc(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_uint8), ("in0", ctypes.c_int32), ("in1", ctypes.c_int32), ("in2", ctypes.c_int32),
+                ("out", ctypes.c_int32)]
+
+
 class TfheParams(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int32), ("N", ctypes.c_int32), ("L", ctypes.c_int32), ("bgbit", ctypes.c_int32),
                 ("basebit", ctypes.c_int32), ("iks_t", ctypes.c_int32)]
@@ -17,7 +22,7 @@ ENGINE_SYMBOLS = [
     "tfhe_ctx_create", "tfhe_ctx_destroy", "tfhe_last_error", "tfhe_ctx_load_cloudkey",
     "tfhe_ctx_load_cloudkey_device", "tfhe_bootstrap_batch", "tfhe_gate_batch", "tfhe_blind_rotate_batch",
     "tfhe_cmux_batch", "tfhe_sample_extract_batch", "tfhe_key_switch_batch", "tfhe_bootstrap_batch_device",
-    "tfhe_gate_batch_device", "tfhe_ctx_kernel_launches", "tfhe_ctx_set_timing", "tfhe_ctx_set_blind_rotate_variant", "tfhe_ctx_collect_timing", "tfhe_ctx_algorithmic_bytes_per_bootstrap", "tfhe_version",
+    "tfhe_gate_batch_device", "tfhe_circuit_run", "tfhe_ctx_kernel_launches", "tfhe_ctx_set_timing", "tfhe_ctx_set_blind_rotate_variant", "tfhe_ctx_collect_timing", "tfhe_ctx_algorithmic_bytes_per_bootstrap", "tfhe_version",
 ]
 CLIENT_SYMBOLS = [
     "tfhe_client_secret_key", "tfhe_client_encrypt_bool", "tfhe_client_decrypt_bool", "tfhe_client_encrypt_message",
@@ -52,6 +57,7 @@ def engine():
         lib.tfhe_key_switch_batch.argtypes = [vp, i64, vp, vp]
         lib.tfhe_bootstrap_batch_device.argtypes = [vp, i64, vp, vp, i64, vp, vp]
         lib.tfhe_gate_batch_device.argtypes = [vp, i64, vp, i64, vp, vp, vp, vp, vp]
+        lib.tfhe_circuit_run.argtypes = [vp, i64, i32, i32, vp, vp, i32, vp, vp]
         lib.tfhe_ctx_set_timing.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_set_blind_rotate_variant.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_collect_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 4)]

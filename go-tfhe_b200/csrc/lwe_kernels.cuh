@@ -32,15 +32,6 @@ __device__ __forceinline__ void gate_coeffs(int op, uint32_t& sa, uint32_t& sb, 
   }
 }
 
-// One job = one prepared ciphertext.  job j reads a_idx[j], b_idx[j] rows (indices into the a / b
-// batches) so that MUX can be expanded into its three bootstraps without copying inputs.
-struct PrepJob {
-  const uint32_t* a;
-  const uint32_t* b;
-  uint32_t* out;
-  int op;
-};
-
 // grid.x = count, block = 256.  ops: [nops] with nops in {1,count}.  For MUX gates (op 10) the
 // first-level jobs are AND(a,b) -> out0[g] and ANDNY(a,c) -> out1[g]  (AND(NOT a, c) == ANDNY(a,c)
 // word for word: (0 - a) + c - 1/8).  Non-MUX gates write their prepared ciphertext to out0[g] and
@@ -90,6 +81,35 @@ __global__ void scatter_rows_kernel(const uint32_t* __restrict__ src, const int*
   for (int i = threadIdx.x; i < words; i += blockDim.x) dst[d + i] = src[s + i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Levelised circuits (the caller directly above the path: README.md:78-114 full adder, gates.go:107-114 MUX).
+// Wires live on the device as [wire][instance][n+1]; one launch prepares every (gate of this level) x instance.
+// ---------------------------------------------------------------------------------------------
+struct GateDesc { int op, in0, in1, out; };  // MUX is expanded on the host into AND / ANDNY / OR
+
+__global__ void circuit_prepare_kernel(const GateDesc* __restrict__ gates, long long instances,
+                                       const uint32_t* __restrict__ wires, uint32_t* __restrict__ prep, int n) {
+  const long long j = blockIdx.x;
+  const GateDesc d = gates[j / instances];
+  const long long inst = j % instances;
+  const uint32_t* a = wires + ((size_t)d.in0 * instances + inst) * (n + 1);
+  const uint32_t* b = wires + ((size_t)d.in1 * instances + inst) * (n + 1);
+  uint32_t sa, sb, bias;
+  gate_coeffs(d.op, sa, sb, bias);
+  uint32_t* o = prep + (size_t)j * (n + 1);
+  for (int i = threadIdx.x; i <= n; i += blockDim.x) o[i] = sa * a[i] + sb * b[i] + (i == n ? bias : 0u);
+}
+
+// NOT / COPY on a whole wire (no bootstrap): out = sa * in0
+__global__ void circuit_linear_kernel(GateDesc d, long long instances, uint32_t* __restrict__ wires, int n) {
+  uint32_t sa, sb, bias;
+  gate_coeffs(d.op, sa, sb, bias);
+  const size_t total = (size_t)instances * (n + 1);
+  const uint32_t* a = wires + (size_t)d.in0 * total;
+  uint32_t* o = wires + (size_t)d.out * total;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) o[i] = sa * a[i];
+}
+
 // trlwe/trlwe_ops.go:10-21 with k = 0
 __global__ void sample_extract_kernel(const uint32_t* __restrict__ trlwe, uint32_t* __restrict__ out, int N) {
   const long long g = blockIdx.x;
@@ -109,7 +129,8 @@ __global__ void sample_extract_kernel(const uint32_t* __restrict__ trlwe, uint32
 __global__ void __launch_bounds__(256) key_switch_kernel(const uint32_t* __restrict__ lwe_in,
                                                          const uint32_t* __restrict__ ksk,
                                                          uint32_t* __restrict__ out, int N, int n, int basebit,
-                                                         int t, int stride) {
+                                                         int t, int stride, const GateDesc* __restrict__ out_gates,
+                                                         long long instances) {
   extern __shared__ uint32_t rows[];  // compacted list of non-zero row indices, capacity N*t
   __shared__ int nrows;
   const long long g = blockIdx.x;
@@ -144,7 +165,9 @@ __global__ void __launch_bounds__(256) key_switch_kernel(const uint32_t* __restr
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(ksk + (size_t)rows[r] * stride) + c4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    uint32_t* o = out + (size_t)g * (n + 1);
+    // circuits: job g = (gate of this level, instance) writes wire out_gates[gate].out of that instance
+    const size_t orow = out_gates ? (size_t)out_gates[g / instances].out * instances + (size_t)(g % instances) : (size_t)g;
+    uint32_t* o = out + orow * (n + 1);
     const int c = c4 * 4;
     const uint32_t bterm = src[N];
     if (c + 0 <= n) o[c + 0] = (c + 0 == n ? bterm : 0u) - acc.x;

@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -60,6 +61,7 @@ struct tfhe_ctx {
   Tw4 tw0{};
   cudaStream_t stream = nullptr;  // used by the host-buffer API
   DevBuf prep, lwe1, tmp, prep2, idx_a, idx_b, ops_dev;       // engine scratch
+  DevBuf wires, gate_descs;                                   // circuit runner
   DevBuf h2d_a, h2d_b, h2d_c, h2d_luts, d2h_out, key_stage;   // staging for the host-buffer API
   int64_t launches = 0;
   int sm_count = 0;
@@ -190,12 +192,13 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   return 0;
 }
 
-int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s) {
+int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s,
+                      const GateDesc* out_gates = nullptr, long long instances = 1) {
   if (count == 0) return 0;
   const size_t sm = (size_t)c->P.N * c->P.iks_t * sizeof(uint32_t);
   if (sm > 128 * 1024) return fail(c, TFHE_ERR_ARG, "N * iks_t too large for the key-switch kernel");
   key_switch_kernel<<<(unsigned)count, 256, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
-                                                     c->P.iks_t, c->ksk_stride);
+                                                     c->P.iks_t, c->ksk_stride, out_gates, instances);
   c->launches++;
   CK(c, cudaGetLastError());
   return 0;
@@ -209,7 +212,7 @@ int check_ready(tfhe_ctx* c, bool need_ksk) {
 }
 
 int bootstrap_device(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const uint32_t* d_luts, int64_t nluts,
-                     uint32_t* d_out, cudaStream_t s) {
+                     uint32_t* d_out, cudaStream_t s, const GateDesc* out_gates = nullptr, long long instances = 1) {
   CK(c, c->lwe1.reserve((size_t)count * (c->P.N + 1) * 4));
   tfhe_ctx::StageEv ev{};
   if (c->timing && count > 0) {
@@ -220,7 +223,7 @@ int bootstrap_device(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const uin
   int rc = launch_blind_rotate(c, count, d_ct, d_luts, nluts, c->lwe1.as<uint32_t>(), 1, s);
   if (rc) return rc;
   if (c->timing && count > 0) CK(c, cudaEventRecord(ev.e1, s));
-  rc = launch_key_switch(c, count, c->lwe1.as<uint32_t>(), d_out, s);
+  rc = launch_key_switch(c, count, c->lwe1.as<uint32_t>(), d_out, s, out_gates, instances);
   if (rc) return rc;
   if (c->timing && count > 0) { CK(c, cudaEventRecord(ev.e2, s)); c->ev_live.push_back(ev); }
   return 0;
@@ -307,7 +310,7 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
-  for (DevBuf* b : {&c->prep, &c->lwe1, &c->tmp, &c->prep2, &c->idx_a, &c->idx_b, &c->ops_dev, &c->h2d_a, &c->h2d_b,
+  for (DevBuf* b : {&c->wires, &c->gate_descs, &c->prep, &c->lwe1, &c->tmp, &c->prep2, &c->idx_a, &c->idx_b, &c->ops_dev, &c->h2d_a, &c->h2d_b,
                     &c->h2d_c, &c->h2d_luts, &c->d2h_out, &c->key_stage})
     b->release();
   for (auto* v : {&c->ev_live, &c->ev_free})
@@ -607,6 +610,106 @@ int tfhe_key_switch_batch(tfhe_ctx* c, int64_t count, const uint32_t* lwe_in, ui
   if ((rc = launch_key_switch(c, count, c->h2d_a.as<uint32_t>(), c->d2h_out.as<uint32_t>(), c->stream))) return rc;
   CK(c, cudaMemcpyAsync(ct_out, c->d2h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+
+// ---- levelised circuit runner --------------------------------------------------------------------------
+int tfhe_circuit_run(tfhe_ctx* c, int64_t instances, int32_t n_inputs, int32_t n_gates, const tfhe_gate_desc* gates,
+                     const uint32_t* inputs, int32_t n_outputs, const int32_t* output_wires, uint32_t* outputs) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  if (instances < 0 || n_inputs < 0 || n_gates < 0 || n_outputs < 0 || (n_gates > 0 && !gates) ||
+      (n_inputs > 0 && instances > 0 && !inputs) || (n_outputs > 0 && (!output_wires || (instances > 0 && !outputs))))
+    return fail(c, TFHE_ERR_ARG, "bad circuit arguments");
+  if ((rc = set_device(c))) return rc;
+  // 1. validate (topological order, single assignment), expand MUX, compute depths
+  int n_wires = n_inputs;
+  for (int g = 0; g < n_gates; g++) n_wires = gates[g].out + 1 > n_wires ? gates[g].out + 1 : n_wires;
+  std::vector<int> depth(n_wires, -1);
+  for (int w = 0; w < n_inputs; w++) depth[w] = 0;
+  struct HGate { GateDesc d; int depth; bool linear; };
+  std::vector<HGate> hg;
+  auto ready = [&](int w) { return w >= 0 && w < (int)depth.size() && depth[w] >= 0; };
+  for (int g = 0; g < n_gates; g++) {
+    const tfhe_gate_desc& q = gates[g];
+    if (q.op > TFHE_OP_COPY) return fail(c, TFHE_ERR_ARG, "gate %d: unknown opcode %d", g, (int)q.op);
+    const bool unary = q.op >= TFHE_OP_NOT, mux = q.op == TFHE_OP_MUX;
+    if (!ready(q.in0) || (!unary && !ready(q.in1)) || (mux && !ready(q.in2)))
+      return fail(c, TFHE_ERR_ARG, "gate %d reads a wire that is not an input or an earlier gate's output", g);
+    if (q.out < n_inputs || q.out >= n_wires || depth[q.out] >= 0)
+      return fail(c, TFHE_ERR_ARG, "gate %d: output wire %d is an input or already assigned", g, q.out);
+    if (unary) {
+      hg.push_back({{q.op, q.in0, q.in0, q.out}, depth[q.in0], true});
+      depth[q.out] = depth[q.in0];
+    } else if (mux) {  // OR(AND(a,b), ANDNY(a,c)) — gates.go:107-114 with AND(NOT a, c) == ANDNY(a, c)
+      const int t0 = (int)depth.size(), t1 = t0 + 1;
+      depth.push_back(-1); depth.push_back(-1);
+      const int d1 = 1 + std::max(depth[q.in0], std::max(depth[q.in1], depth[q.in2]));
+      hg.push_back({{TFHE_OP_AND, q.in0, q.in1, t0}, d1, false});
+      hg.push_back({{TFHE_OP_ANDNY, q.in0, q.in2, t1}, d1, false});
+      hg.push_back({{TFHE_OP_OR, t0, t1, q.out}, d1 + 1, false});
+      depth[t0] = depth[t1] = d1;
+      depth[q.out] = d1 + 1;
+    } else {
+      const int d1 = 1 + std::max(depth[q.in0], depth[q.in1]);
+      hg.push_back({{q.op, q.in0, q.in1, q.out}, d1, false});
+      depth[q.out] = d1;
+    }
+  }
+  for (int k = 0; k < n_outputs; k++)
+    if (!ready(output_wires[k])) return fail(c, TFHE_ERR_ARG, "output %d names an unassigned wire", k);
+  if (instances == 0) return TFHE_OK;
+  const int total_wires = (int)depth.size();
+  int max_depth = 0;
+  for (auto& h : hg) max_depth = std::max(max_depth, h.depth);
+  // 2. device state
+  const int n1 = c->P.n + 1;
+  const size_t wire_bytes = (size_t)instances * n1 * 4;
+  CK(c, c->wires.reserve((size_t)total_wires * wire_bytes));
+  cudaStream_t s = c->stream;
+  if (n_inputs) CK(c, cudaMemcpyAsync(c->wires.p, inputs, (size_t)n_inputs * wire_bytes, cudaMemcpyHostToDevice, s));
+  std::vector<GateDesc> sorted;  // bootstrapped gates grouped by depth
+  std::vector<int> level_off(max_depth + 2, 0);
+  size_t widest = 0;
+  for (int d = 1; d <= max_depth; d++) {
+    level_off[d] = (int)sorted.size();
+    for (auto& h : hg) if (!h.linear && h.depth == d) sorted.push_back(h.d);
+    widest = std::max(widest, sorted.size() - (size_t)level_off[d]);
+  }
+  level_off[max_depth + 1] = (int)sorted.size();
+  if (!sorted.empty()) {
+    CK(c, c->gate_descs.reserve(sorted.size() * sizeof(GateDesc)));
+    CK(c, cudaMemcpyAsync(c->gate_descs.p, sorted.data(), sorted.size() * sizeof(GateDesc), cudaMemcpyHostToDevice, s));
+    CK(c, c->prep.reserve(widest * wire_bytes));
+  }
+  // 3. run: depth d = linear gates whose input has depth d (in list order), then the bootstrapped gates of depth d+1
+  auto run_linear = [&](int d) -> int {
+    for (auto& h : hg)
+      if (h.linear && h.depth == d) {
+        circuit_linear_kernel<<<256, 256, 0, s>>>(h.d, instances, c->wires.as<uint32_t>(), c->P.n);
+        c->launches++;
+      }
+    CK(c, cudaGetLastError());
+    return 0;
+  };
+  if ((rc = run_linear(0))) return rc;
+  for (int d = 1; d <= max_depth; d++) {
+    const int ng = level_off[d + 1] - level_off[d];
+    if (ng > 0) {
+      const GateDesc* dg = c->gate_descs.as<GateDesc>() + level_off[d];
+      const int64_t jobs = (int64_t)ng * instances;
+      circuit_prepare_kernel<<<(unsigned)jobs, 256, 0, s>>>(dg, instances, c->wires.as<uint32_t>(), c->prep.as<uint32_t>(), c->P.n);
+      c->launches++;
+      CK(c, cudaGetLastError());
+      if ((rc = bootstrap_device(c, jobs, c->prep.as<uint32_t>(), nullptr, 0, c->wires.as<uint32_t>(), s, dg, instances))) return rc;
+    }
+    if ((rc = run_linear(d))) return rc;
+  }
+  for (int k = 0; k < n_outputs; k++)
+    CK(c, cudaMemcpyAsync(outputs + (size_t)k * instances * n1, c->wires.as<char>() + (size_t)output_wires[k] * wire_bytes, wire_bytes,
+                          cudaMemcpyDeviceToHost, s));
+  CK(c, cudaStreamSynchronize(s));
   return TFHE_OK;
 }
 

@@ -136,6 +136,20 @@ class Context:
         self._ck(self.lib.tfhe_key_switch_batch(self.h, len(x), _ptr(x), _ptr(out)), "tfhe_key_switch_batch")
         return out
 
+    def circuit_run(self, gates, n_inputs, inputs, output_wires):
+        """gates: list of (op, in0, in1, in2, out); inputs [n_inputs][instances][n+1] -> [n_outputs][instances][n+1]."""
+        P = self.P
+        inputs = _u32(inputs).reshape(n_inputs, -1, P.n + 1)
+        instances = inputs.shape[1]
+        arr = (_native.GateDesc * max(len(gates), 1))()
+        for k, (op, i0, i1, i2, o) in enumerate(gates):
+            arr[k] = _native.GateDesc(OPCODES[op.upper()] if isinstance(op, str) else int(op), i0, i1, i2, o)
+        ow = np.ascontiguousarray(output_wires, dtype=np.int32)
+        out = np.empty((len(ow), instances, P.n + 1), dtype=np.uint32)
+        self._ck(self.lib.tfhe_circuit_run(self.h, instances, n_inputs, len(gates), ctypes.cast(arr, ctypes.c_void_p),
+                                           _ptr(inputs), len(ow), _ptr(ow), _ptr(out)), "tfhe_circuit_run")
+        return out
+
     # --- device-buffer hot path (pointers are ints) ---------------------------------------------------
     def bootstrap_batch_device(self, count, d_ct_in, d_ct_out, d_luts=None, nluts=0, stream=0):
         self._ck(self.lib.tfhe_bootstrap_batch_device(self.h, count, d_ct_in, d_luts, nluts, d_ct_out, stream),

@@ -125,6 +125,21 @@ int tfhe_sample_extract_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* trlw
  * LWE [count][N+1] -> LWE [count][n+1]. */
 int tfhe_key_switch_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* lwe_in, uint32_t* ct_out);
 
+/* --- levelised circuits (additive: the caller immediately above the path) ------------------------------- */
+/* One gate of a circuit over wire ids.  Wires 0..n_inputs-1 are the inputs; every gate writes a distinct wire
+ * >= n_inputs and may read only inputs or wires written by EARLIER gates of the list (topological order).
+ * in2 is read by TFHE_OP_MUX only; in1 is ignored by NOT / COPY. */
+typedef struct { uint8_t op; int32_t in0, in1, in2, out; } tfhe_gate_desc;
+
+/* Evaluates the same circuit on `instances` independent input sets.  The engine levelises the gate list
+ * (depth = 1 + max depth of the operands; NOT/COPY cost no level; MUX = OR(AND(a,b), AND(NOT a, c)) as in
+ * gates/gates.go:107-114) and runs each level as ONE batch of (gates of the level) x instances bootstraps with all
+ * intermediate wires resident on the device.  Every gate computes exactly what gates.X of the reference computes
+ * (e.g. the full adder of README.md:78-87), so results are bit-identical to running the gates one by one.
+ * inputs: [n_inputs][instances][n+1]; outputs: [n_outputs][instances][n+1] (wire output_wires[k]). */
+int tfhe_circuit_run(tfhe_ctx* ctx, int64_t instances, int32_t n_inputs, int32_t n_gates, const tfhe_gate_desc* gates,
+                     const uint32_t* inputs, int32_t n_outputs, const int32_t* output_wires, uint32_t* outputs);
+
 /* --- the hot path, device buffers (inputs already resident in HBM) -------------------------- */
 /* Same semantics; pointers are device pointers on the context's device; work is enqueued on
  * `stream` (cudaStream_t, 0 = default) and NOT synchronised. */

@@ -128,3 +128,12 @@ def test_gates_constant_and_not(T):
     ct = T.tlwe.EncryptBool([1, 0], sk, 2)
     assert list(T.tlwe.DecryptBool(T.gates.NOT(ct), sk)) == [0, 1]
     assert np.array_equal(T.gates.Copy(ct), ct)
+
+
+def test_circuit_builder_bookkeeping(T):
+    c = T.circuit.ripple_carry_adder(8)
+    assert c.n_inputs == 16 and c.n_bootstraps == 40 and len(c.out_wires) == 8
+    assert c.n_levels == 17  # bit 0: XOR/AND at depth 1, carry at 3; every further bit adds 2 levels
+    m = T.circuit.Circuit(3)
+    m.outputs([m.gate("MUX", 0, 1, 2)])
+    assert m.n_bootstraps == 3 and m.n_levels == 2

@@ -236,3 +236,45 @@ def test_full_size_batch_properties(T, gpu):
     got = ctx.gate_batch("NAND", a, b)
     assert np.array_equal(sk.decrypt_bool(got), 1 - (A & B))
     assert np.array_equal(got[0], got[4095])
+
+
+def test_circuit_full_adder_and_ripple_carry_bit_exact(T, O, gpu):
+    """Levelised circuit runner (tfhe_circuit_run) == the reference's gate-by-gate evaluation (README.md:78-114):
+    every wire is produced by the same gates.X arithmetic, so outputs are bit-identical to chaining single gates."""
+    P, sk, ck, ctx = gpu("80")
+    bits, inst = 3, 5
+    rng = np.random.default_rng(4)
+    x, y = rng.integers(0, 1 << bits, inst), rng.integers(0, 1 << bits, inst)
+    circ = T.circuit.ripple_carry_adder(bits)
+    assert circ.n_bootstraps == 5 * bits
+    ins = np.stack([sk.encrypt_bool((x >> i) & 1, 300 + i) for i in range(bits)] +
+                   [sk.encrypt_bool((y >> i) & 1, 400 + i) for i in range(bits)])
+    cst = np.broadcast_to(O.constant(P, False), (1, inst, P.n + 1))
+    got = ctx.circuit_run(circ.gates, 2 * bits + 1, np.concatenate([ins, cst]), circ.out_wires)
+    s = sum(sk.decrypt_bool(got[i]).astype(np.int64) << i for i in range(bits))
+    assert np.array_equal(s, (x + y) % (1 << bits))
+    # oracle, gate by gate in list order
+    wires = {w: ins[w] for w in range(2 * bits)}
+    wires[2 * bits] = cst[0]
+    for op, a, b, c, o in circ.gates:
+        wires[o] = O.gate_batch(ck, op, wires[a], wires[b])
+    for k, w in enumerate(circ.out_wires):
+        assert np.array_equal(got[k], wires[w])
+
+
+def test_circuit_mux_not_copy_and_errors(T, O, gpu):
+    P, sk, ck, ctx = gpu("80")
+    A, B, C = [0, 1, 0, 1], [1, 1, 0, 0], [0, 0, 1, 1]
+    ins = np.stack([sk.encrypt_bool(A, 1), sk.encrypt_bool(B, 2), sk.encrypt_bool(C, 3)])
+    gates_ = [("NOT", 0, 0, 0, 3), ("MUX", 3, 1, 2, 4), ("COPY", 4, 4, 0, 5), ("XNOR", 5, 0, 0, 6)]
+    got = ctx.circuit_run(gates_, 3, ins, [4, 5, 6, 3])
+    na = [1 - a for a in A]
+    mux = [b if x else c for x, b, c in zip(na, B, C)]
+    assert list(sk.decrypt_bool(got[0])) == mux and list(sk.decrypt_bool(got[1])) == mux
+    assert list(sk.decrypt_bool(got[2])) == [1 - (m ^ a) for m, a in zip(mux, A)]
+    assert np.array_equal(got[3], O.NOT(ins[0]))
+    assert np.array_equal(got[0], O.mux(ck, O.NOT(ins[0]), ins[1], ins[2]))
+    with pytest.raises(T.TfheError):  # reads a wire that is not yet assigned
+        ctx.circuit_run([("AND", 0, 5, 0, 3)], 3, ins, [3])
+    with pytest.raises(T.TfheError):  # writes an input wire
+        ctx.circuit_run([("AND", 0, 1, 0, 2)], 3, ins, [2])
