@@ -30,6 +30,14 @@
 #ifndef TFHE_BR_KEEP_OWN
 #define TFHE_BR_KEEP_OWN 0      // 1: exchanges keep the one point that does not change owner in its register (measured 3.5% slower: the predicated asm blocks pin the schedule)
 #endif
+#ifndef TFHE_BR_PAIR_INV
+#define TFHE_BR_PAIR_INV 0      // 1: the two inverse transforms of a step run interleaved, sharing their exchanges (measured: no gain)
+#endif
+#ifndef TFHE_BR_PAIR_FWD
+#define TFHE_BR_PAIR_FWD 0      // forward transforms of consecutive decomposition levels run interleaved in pairs
+#endif
+// exchange buffers hold one transform ([2][M]) unless a paired mode needs two ([2][2M])
+#define TFHE_BR_EXW ((TFHE_BR_PAIR_INV || TFHE_BR_PAIR_FWD) ? 2 : 1)
 #define TFHE_PRAGMA_(x) _Pragma(#x)
 #define TFHE_UNROLL(n) TFHE_PRAGMA_(unroll n)
 
@@ -241,7 +249,7 @@ struct Fft {
       mbar_wait(rd_bar, rd_phase);  // every thread has finished reading the previous exchange
       rd_phase ^= 1u;
     } else {
-      buf += (parity ? G::M : 0);
+      buf += (parity ? TFHE_BR_EXW * G::M : 0);
       parity ^= 1;
     }
     const int wb = G::base(KW, tau), rb = G::base(KR, tau);
@@ -265,6 +273,29 @@ struct Fft {
   }
   template <int KW, int KR>
   __device__ __forceinline__ void exchange(double2 (&x)[8]) { exchange<KW, KR>(x, NoHook()); }
+
+  // Two independent transforms exchanged together: one block barrier for both, and twice the independent work
+  // between barriers (the buffers are [2 parities][2 transforms][M]).  Not available in SINGLE mode.
+  template <int KW, int KR>
+  __device__ __forceinline__ void exchange2(double2 (&x)[8], double2 (&y)[8]) {
+    static_assert(!SINGLE && TFHE_BR_EXW == 2, "paired exchange needs the double-width ping-pong buffers");
+    double2* buf = ex + (parity ? 2 * G::M : 0);
+    parity ^= 1;
+    const int wb = G::base(KW, tau), rb = G::base(KR, tau);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int p = swz(wb + G::stride(KW) * a);
+      buf[p] = x[a];
+      buf[G::M + p] = y[a];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int p = swz(rb + G::stride(KR) * a);
+      x[a] = buf[p];
+      y[a] = buf[G::M + p];
+    }
+  }
 
   template <int K>
   __device__ __forceinline__ void fwd_pass(double2 (&x)[8], const Tw4& tw0) {
@@ -316,6 +347,20 @@ struct Fft {
     inv_pass<0>(x, tw0);
   }
   __device__ __forceinline__ void inverse(double2 (&x)[8], const Tw4& tw0) { inverse(x, tw0, NoHook()); }
+
+  // paired versions: the same passes on two independent arrays, exchanges shared
+  __device__ __forceinline__ void forward2(double2 (&x)[8], double2 (&y)[8], const Tw4& tw0) {
+    fwd_pass<0>(x, tw0); fwd_pass<0>(y, tw0);
+    if constexpr (G::NPASS > 1) { exchange2<0, 1>(x, y); fwd_pass<1>(x, tw0); fwd_pass<1>(y, tw0); }
+    if constexpr (G::NPASS > 2) { exchange2<1, 2>(x, y); fwd_pass<2>(x, tw0); fwd_pass<2>(y, tw0); }
+    if constexpr (G::NPASS > 3) { exchange2<2, 3>(x, y); fwd_pass<3>(x, tw0); fwd_pass<3>(y, tw0); }
+  }
+  __device__ __forceinline__ void inverse2(double2 (&x)[8], double2 (&y)[8], const Tw4& tw0) {
+    if constexpr (G::NPASS > 3) { inv_pass<3>(x, tw0); inv_pass<3>(y, tw0); exchange2<3, 2>(x, y); }
+    if constexpr (G::NPASS > 2) { inv_pass<2>(x, tw0); inv_pass<2>(y, tw0); exchange2<2, 1>(x, y); }
+    if constexpr (G::NPASS > 1) { inv_pass<1>(x, tw0); inv_pass<1>(y, tw0); exchange2<1, 0>(x, y); }
+    inv_pass<0>(x, tw0); inv_pass<0>(y, tw0);
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -369,10 +414,30 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
                                                  int at, uint32_t offset, const Tw4& tw0) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
   constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
   const int tau = fft.tau;
   double2 accA[8], accB[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
+
+  // spectrum of one digit polynomial times key row r, accumulated into both output spectra
+  auto mac = [&](const double2 (&x)[8], int r) {
+    const int rowA = (r * 2 + 0) * M + tau;
+    const int rowB = rowA + M;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const double2 ka = bk(rowA + e * T);
+      const double2 kb = bk(rowB + e * T);
+      accA[e].x = fma(x[e].x, ka.x, accA[e].x);
+      accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
+      accA[e].y = fma(x[e].x, ka.y, accA[e].y);
+      accA[e].y = fma(x[e].y, ka.x, accA[e].y);
+      accB[e].x = fma(x[e].x, kb.x, accB[e].x);
+      accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
+      accB[e].y = fma(x[e].x, kb.y, accB[e].y);
+      accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+    }
+  };
 
   TFHE_UNROLL(TFHE_BR_UNROLL_POLY)
   for (int poly = 0; poly < 2; poly++) {
@@ -385,42 +450,48 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
       dre[a] = rot_read<N>(P, ib + T * a) - P[j] + offset;
       dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + offset;
     }
-    TFHE_UNROLL(TFHE_BR_UNROLL_LVL)
-    for (int lvl = 0; lvl < L; lvl++) {
-      double2 x[8];
-      constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+    auto digits = [&](double2 (&x)[8], int lvl) {
       const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
       for (int a = 0; a < 8; a++) {
         x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
         x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
       }
-      fft.forward(x, tw0);
-      const int rowA = ((poly * L + lvl) * 2 + 0) * M + tau;
-      const int rowB = rowA + M;
+    };
+    int lvl = 0;
+#if TFHE_BR_PAIR_FWD
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const double2 ka = bk(rowA + e * T);
-        const double2 kb = bk(rowB + e * T);
-        accA[e].x = fma(x[e].x, ka.x, accA[e].x);
-        accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
-        accA[e].y = fma(x[e].x, ka.y, accA[e].y);
-        accA[e].y = fma(x[e].y, ka.x, accA[e].y);
-        accB[e].x = fma(x[e].x, kb.x, accB[e].x);
-        accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
-        accB[e].y = fma(x[e].x, kb.y, accB[e].y);
-        accB[e].y = fma(x[e].y, kb.x, accB[e].y);
-      }
+    for (; lvl + 1 < L; lvl += 2) {
+      double2 x[8], y[8];
+      digits(x, lvl);
+      digits(y, lvl + 1);
+      fft.forward2(x, y, tw0);
+      mac(x, poly * L + lvl);
+      mac(y, poly * L + lvl + 1);
+    }
+#endif
+    TFHE_UNROLL(TFHE_BR_UNROLL_LVL)
+    for (; lvl < L; lvl++) {
+      double2 x[8];
+      digits(x, lvl);
+      fft.forward(x, tw0);
+      mac(x, poly * L + lvl);
     }
   }
+#if TFHE_BR_PAIR_INV
+  fft.inverse2(accA, accB, tw0);
+#else
   fft.inverse(accA, tw0);
+#endif
 #pragma unroll
   for (int a = 0; a < 8; a++) {
     const int j = tau + T * a;
     acc[j] += to_torus<SMALL>(accA[a].x);
     acc[j + M] += to_torus<SMALL>(accA[a].y);
   }
+#if !TFHE_BR_PAIR_INV
   fft.inverse(accB, tw0);
+#endif
 #pragma unroll
   for (int a = 0; a < 8; a++) {
     const int j = tau + T * a;
@@ -431,7 +502,7 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
 
 template <int LOGN>
 constexpr size_t br_smem_bytes(int n) {
-  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * (1 << (LOGN - 1)) * 16 /*exchange*/ +
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [2][EXW][M]*/ +
          (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
 }
 
@@ -443,8 +514,8 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_kernel(c
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
-  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][M]
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 32 * M);
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][EXW][M]
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 32 * TFHE_BR_EXW * M);
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   const int n = A.n;
@@ -644,7 +715,7 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const Cmu
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);       // holds ct0, becomes the result
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);
-  uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 32 * M);  // [2][N]
+  uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 32 * TFHE_BR_EXW * M);  // [2][N]
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   for (int j = tau; j < 2 * N; j += T) {

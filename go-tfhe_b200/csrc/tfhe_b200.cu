@@ -167,7 +167,7 @@ int find_variant(const tfhe_params& P) {
   return -1;
 }
 
-size_t cmux_smem(int N) { return (size_t)8 * N + (size_t)16 * N + (size_t)8 * N; }
+size_t cmux_smem(int N) { return (size_t)8 * N + (size_t)32 * N + (size_t)8 * N; }
 
 int set_device(tfhe_ctx* c) {
   CK(c, cudaSetDevice(c->device));

@@ -1,7 +1,8 @@
 #!/bin/bash
-# A/B of the three key-fetch variants of the blind-rotate kernel (+ any experimental engine builds)
-for v in ldg tma tex; do
-  echo "== TFHE_B200_BR=$v"; TFHE_B200_BR=$v python tools/gpu_quick.py 128 4096 2>&1 | tail -2
+# A/B harness: default engine (optionally all key-fetch variants) + any experimental engine builds (lib/exp_*.so)
+VARIANTS=${VARIANTS:-ldg}
+for v in $VARIANTS; do
+  echo "== default lib, TFHE_B200_BR=$v"; TFHE_B200_BR=$v python tools/gpu_quick.py 128 4096 2>&1 | tail -2
 done
 for so in go-tfhe_b200/lib/exp_*.so; do
   [ -e "$so" ] || continue
