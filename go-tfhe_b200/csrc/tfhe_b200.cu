@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "blind_rotate.cuh"
+#include "blind_rotate_w16.cuh"
 #include "lwe_kernels.cuh"
 
 using namespace tfhe;
@@ -71,6 +72,10 @@ struct tfhe_ctx {
   // shared memory (cp.async.bulk + mbarrier), 2 = texture fetches.  See profiles/ for the measurements behind the default.
   int br_variant = 0;
   cudaTextureObject_t bsk_tex = 0;
+  // warp-per-gate kernel (N = 1024 only): its own key layout and twiddle tables
+  double2* d_bsk16 = nullptr;
+  double2* d_tw16 = nullptr;   // [8][16] pass-1 twiddles then [4][32] last-stage twiddles
+  Tw8 tw0_16{};
   bool timing = false;
   struct StageEv { cudaEvent_t e0, e1, e2; };
   std::vector<StageEv> ev_live, ev_free;
@@ -136,9 +141,28 @@ struct Variant {
   void (*cmux)(const CmuxArgs);
   size_t (*br_smem)(int n);
   size_t (*br_staged_smem)(int n);
+  void (*br_w16)(const BrW16Args);   // warp-per-gate, TMEM accumulators (N = 1024 only, else nullptr)
+  void (*br_tm)(const BrArgs);       // block-per-gate, TMEM accumulators (N >= 1024, else nullptr)
 };
 template <int LOGN> size_t br_smem(int n) { return br_smem_bytes<LOGN>(n); }
 template <int LOGN> size_t br_staged_smem(int n) { return br_staged_smem_bytes<LOGN>(n); }
+#ifndef TFHE_BR_W16_MINB
+#define TFHE_BR_W16_MINB 2
+#endif
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto w16_kernel() -> void (*)(const BrW16Args) {
+  if constexpr (LOGN == 10) return blind_rotate_w16_kernel<L, BG, SMALL, TFHE_BR_W16_MINB>;
+  else return nullptr;
+}
+#ifndef TFHE_BR_TM_MINB_N1024
+#define TFHE_BR_TM_MINB_N1024 6
+#endif
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto tm_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10) return blind_rotate_tm_kernel<LOGN, L, BG, SMALL, TFHE_BR_TM_MINB_N1024>;
+  else if constexpr (LOGN == 11) return blind_rotate_tm_kernel<LOGN, L, BG, SMALL, 3>;
+  else return nullptr;
+}
 #ifndef TFHE_BR_STAGED_MINB_N1024
 #define TFHE_BR_STAGED_MINB_N1024 4
 #endif
@@ -146,7 +170,7 @@ template <int LOGN> size_t br_staged_smem(int n) { return br_staged_smem_bytes<L
   { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>,                              \
     blind_rotate_kernel<LOGN, L, BG, SMALL, MINB, true>,                                            \
     blind_rotate_staged_kernel<LOGN, L, BG, SMALL, MINBS>, cmux_kernel<LOGN, L, BG, SMALL, MINB>,   \
-    br_smem<LOGN>, br_staged_smem<LOGN> }
+    br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>() }
 #ifndef TFHE_BR_MINB_N1024
 #define TFHE_BR_MINB_N1024 4
 #endif
@@ -183,8 +207,19 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   a.ct_in = d_ct; a.testvec = c->d_testvec; a.luts = d_luts; a.nluts = nluts; a.bsk = c->d_bsk; a.tw_tab = c->d_tw;
   a.out = d_out; a.n = c->P.n; a.offset = c->offset; a.out_mode = out_mode; a.tw0 = c->tw0;
   const int T = c->P.N / 16;
+  if (c->br_variant == 3 && V.br_w16 && c->d_bsk16) {
+    BrW16Args w{};
+    w.ct_in = d_ct; w.testvec = c->d_testvec; w.luts = d_luts; w.nluts = nluts; w.count = count; w.bsk = c->d_bsk16;
+    w.tw1 = c->d_tw16; w.twl = c->d_tw16 + 8 * 16; w.out = d_out; w.n = c->P.n; w.offset = c->offset; w.out_mode = out_mode;
+    w.tw0 = c->tw0_16;
+    V.br_w16<<<(unsigned)((count + 3) / 4), 128, br_w16_smem_bytes(c->P.n), s>>>(w);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+  }
   a.bsk_tex = c->bsk_tex;
-  if (c->br_variant == 1) V.br_staged<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
+  if (c->br_variant == 4 && V.br_tm) V.br_tm<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  else if (c->br_variant == 1) V.br_staged<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 2) V.br_tex<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   else V.br<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   c->launches++;
@@ -288,6 +323,29 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
   const Variant& V = kVariants[v];
+  if (V.br_tm && (e = cudaFuncSetAttribute(V.br_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_tm)", e);
+  if (V.br_w16) {
+    const int M = 512;
+    auto blk = [&](int m, int i, double2* o) {
+      o[0] = twiddle(M, m, i); o[1] = twiddle(M, 2 * m, 2 * i); o[2] = twiddle(M, 4 * m, 4 * i); o[3] = twiddle(M, 4 * m, 4 * i + 2);
+      for (int j = 0; j < 4; j++) o[4 + j] = twiddle(M, 8 * m, 8 * i + 2 * j);
+    };
+    blk(1, 0, c->tw0_16.s);
+    std::vector<double2> t16(8 * 16 + 4 * 32);
+    for (int b = 0; b < 16; b++) {
+      double2 o[8];
+      blk(16, b, o);
+      for (int j = 0; j < 8; j++) t16[j * 16 + b] = o[j];
+    }
+    for (int lane = 0; lane < 32; lane++)
+      for (int j = 0; j < 4; j++) t16[8 * 16 + j * 32 + lane] = twiddle(M, 256, 8 * lane + 2 * j);
+    if ((e = cudaMalloc(&c->d_tw16, t16.size() * sizeof(double2))) != cudaSuccess) return bail("cudaMalloc(twiddles16)", e);
+    if ((e = cudaMemcpy(c->d_tw16, t16.data(), t16.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return bail("cudaMemcpy(twiddles16)", e);
+    if ((e = cudaFuncSetAttribute(V.br_w16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_w16_smem_bytes(4096))) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(blind_rotate_w16)", e);
+  }
   if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)  // limit, not allocation: n <= 4096
     return bail("cudaFuncSetAttribute(blind_rotate)", e);
   if ((e = cudaFuncSetAttribute(V.br_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_staged_smem(4096))) !=
@@ -296,7 +354,7 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
   if (const char* sel = getenv("TFHE_B200_BR"))
-    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : 0;
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
   if ((e = cudaFuncSetAttribute(key_switch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -317,6 +375,8 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
     for (auto& ev : *v) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); cudaEventDestroy(ev.e2); }
   if (c->bsk_tex) cudaDestroyTextureObject(c->bsk_tex);
   if (c->d_bsk) cudaFree(c->d_bsk);
+  if (c->d_bsk16) cudaFree(c->d_bsk16);
+  if (c->d_tw16) cudaFree(c->d_tw16);
   if (c->d_ksk) cudaFree(c->d_ksk);
   if (c->d_testvec) cudaFree(c->d_testvec);
   if (c->d_tw) cudaFree(c->d_tw);
@@ -337,6 +397,12 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
   bsk_repack_kernel<<<(unsigned)polys, 128, 0, s>>>(d_bsk_fft, c->d_bsk, P.N);
   c->launches++;
   CK(c, cudaGetLastError());
+  if (kVariants[c->variant].br_w16) {
+    if (!c->d_bsk16) CK(c, cudaMalloc(&c->d_bsk16, polys * M * sizeof(double2)));
+    bsk_repack_w16_kernel<<<(unsigned)polys, 128, 0, s>>>(d_bsk_fft, c->d_bsk16);
+    c->launches++;
+    CK(c, cudaGetLastError());
+  }
   CK(c, cudaMemcpyAsync(c->d_testvec, d_testvec, (size_t)2 * P.N * 4, cudaMemcpyDeviceToDevice, s));
   if (d_ksk) {
     const size_t rows = (size_t)P.N * P.iks_t * (1u << P.basebit);
@@ -717,7 +783,9 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) { return c ? c->launches : 0
 
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;
-  if (variant < 0 || variant > 2) return fail(c, TFHE_ERR_ARG, "variant must be 0 (ldg), 1 (tma) or 2 (tex)");
+  if (variant < 0 || variant > 4) return fail(c, TFHE_ERR_ARG, "variant must be 0 (ldg), 1 (tma), 2 (tex), 3 (w16) or 4 (tmem)");
+  if (variant == 4 && !kVariants[c->variant].br_tm) return fail(c, TFHE_ERR_ARG, "the TMEM-accumulator kernel needs N >= 1024");
+  if (variant == 3 && !kVariants[c->variant].br_w16) return fail(c, TFHE_ERR_ARG, "the warp-per-gate kernel exists for N = 1024 only");
   if (variant == 2 && c->key_loaded && !c->bsk_tex) return fail(c, TFHE_ERR_STATE, "no texture object");
   c->br_variant = variant;
   return TFHE_OK;

@@ -81,9 +81,17 @@ def test_key_fetch_variants_agree(O, gpu, name):
         for v in ("ldg", "tma", "tex"):
             ctx.set_blind_rotate_variant(v)
             outs[v] = ctx.blind_rotate_batch(ct)
+        if P.N == 1024:  # warp-per-gate kernel with TMEM accumulators: a different transform schedule, same exact result
+            ctx.set_blind_rotate_variant("w16")
+            outs["w16"] = ctx.blind_rotate_batch(ct)
+        ctx.set_blind_rotate_variant("tmem")  # block-per-gate kernel with the accumulators in TMEM
+        outs["tmem"] = ctx.blind_rotate_batch(ct)
     finally:
         ctx.set_blind_rotate_variant("ldg")
     assert np.array_equal(outs["ldg"], outs["tma"]) and np.array_equal(outs["ldg"], outs["tex"])
+    if "w16" in outs:
+        assert np.array_equal(outs["ldg"], outs["w16"])
+    assert np.array_equal(outs["ldg"], outs["tmem"])
     if name == "80":
         ev = O.Evaluator(P.N)
         want = np.stack([ev.blind_rotate(P, c, ck.testvec, ck.bsk_fft, ck.offset) for c in ct])

@@ -6,6 +6,6 @@ for v in $VARIANTS; do
 done
 for so in go-tfhe_b200/lib/exp_*.so; do
   [ -e "$so" ] || continue
-  echo "== $so"
-  TFHE_B200_LIB=$PWD/$so python tools/gpu_quick.py 128 4096 2>&1 | tail -2
+  echo "== $so (TFHE_B200_BR=${EXPBR:-ldg})"
+  TFHE_B200_BR=${EXPBR:-ldg} TFHE_B200_LIB=$PWD/$so python tools/gpu_quick.py 128 4096 2>&1 | tail -2
 done
