@@ -20,6 +20,9 @@
 
 #include "blind_rotate.cuh"
 
+#ifndef TFHE_TM_BK_SPLIT
+#define TFHE_TM_BK_SPLIT 0
+#endif
 #ifndef TFHE_W16_PREFETCH
 #define TFHE_W16_PREFETCH 1
 #endif
@@ -472,6 +475,47 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
         fft.forward(x, A.tw0);
         const double2* __restrict__ rowA = bk + (size_t)(r * 2 + 0) * M;
         const double2* __restrict__ rowB = rowA + M;
+#if TFHE_TM_BK_SPLIT
+        // key values and accumulator columns one half (4 points) at a time, next half in flight: 32 + 32 registers
+        double2 ka[2][4], kb[2][4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { ka[0][q] = __ldg(rowA + q * T); kb[0][q] = __ldg(rowB + q * T); }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if (h == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { ka[1][q] = __ldg(rowA + (4 + q) * T); kb[1][q] = __ldg(rowB + (4 + q) * T); }
+          }
+          double2 aA[4], aB[4];
+          uint32_t ra[16], rb[16];
+          if (r > 0) {
+            tmem_ld16(tacc + 16 * h, ra);
+            tmem_ld16(tacc + 32 + 16 * h, rb);
+            tmem_wait_ld();
+            unpack4(ra, aA);
+            unpack4(rb, aB);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { aA[q] = make_double2(0.0, 0.0); aB[q] = make_double2(0.0, 0.0); }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int e = 4 * h + q;
+            aA[q].x = fma(x[e].x, ka[h][q].x, aA[q].x);
+            aA[q].x = fma(-x[e].y, ka[h][q].y, aA[q].x);
+            aA[q].y = fma(x[e].x, ka[h][q].y, aA[q].y);
+            aA[q].y = fma(x[e].y, ka[h][q].x, aA[q].y);
+            aB[q].x = fma(x[e].x, kb[h][q].x, aB[q].x);
+            aB[q].x = fma(-x[e].y, kb[h][q].y, aB[q].x);
+            aB[q].y = fma(x[e].x, kb[h][q].y, aB[q].y);
+            aB[q].y = fma(x[e].y, kb[h][q].x, aB[q].y);
+          }
+          pack4(aA, ra);
+          pack4(aB, rb);
+          tmem_st16(tacc + 16 * h, ra);
+          tmem_st16(tacc + 32 + 16 * h, rb);
+        }
+#else
         double2 ka[8], kb[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) { ka[e] = __ldg(rowA + e * T); kb[e] = __ldg(rowB + e * T); }  // all 16 in flight
@@ -506,6 +550,7 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
           tmem_st16(tacc + 16 * h, ra);
           tmem_st16(tacc + 32 + 16 * h, rb);
         }
+#endif
         tmem_wait_st();
       }
     }
