@@ -25,6 +25,7 @@ import (
 	"github.com/thedonutfactory/go-tfhe/cloudkey"
 	"github.com/thedonutfactory/go-tfhe/params"
 	"github.com/thedonutfactory/go-tfhe/tlwe"
+	"github.com/thedonutfactory/go-tfhe/trgsw"
 	"github.com/thedonutfactory/go-tfhe/trlwe"
 )
 
@@ -72,6 +73,26 @@ func For(ck *cloudkey.CloudKey) *Engine {
 	engines[ck] = e
 	return e
 }
+
+// ForParts serves the evaluator.* entry points, which receive the pieces of a CloudKey instead of the struct
+// (evaluator/evaluator.go:139): engines are cached by the identity of the bootstrapping-key slice.
+func ForParts(bsk []*trgsw.TRGSWLv1FFT, ksk []*tlwe.TLWELv0, offset params.Torus, testvec *trlwe.TRLWELv1) *Engine {
+	enginesMu.Lock()
+	defer enginesMu.Unlock()
+	key := &bsk[0]
+	if e, ok := partEngines[key]; ok {
+		return e
+	}
+	if testvec == nil {
+		testvec = trlwe.NewTRLWELv1()
+	}
+	e := New(&cloudkey.CloudKey{DecompositionOffset: offset, BlindRotateTestvec: testvec, KeySwitchingKey: ksk,
+		BootstrappingKey: bsk}, 0)
+	partEngines[key] = e
+	return e
+}
+
+var partEngines = map[**trgsw.TRGSWLv1FFT]*Engine{}
 
 // New flattens ck (cloudkey/cloudkey.go:16-21) and uploads it to `device`.
 func New(ck *cloudkey.CloudKey, device int) *Engine {
