@@ -30,6 +30,9 @@
 #ifndef TFHE_BR_KEEP_OWN
 #define TFHE_BR_KEEP_OWN 0      // 1: exchanges keep the one point that does not change owner in its register (measured 3.5% slower: the predicated asm blocks pin the schedule)
 #endif
+#ifndef TFHE_BR_SHFL_LAST
+#define TFHE_BR_SHFL_LAST 1     // N = 2048: last radix-2 stage through a lane-pair shuffle instead of a third exchange
+#endif
 #ifndef TFHE_BR_PAIR_INV
 #define TFHE_BR_PAIR_INV 0      // 1: the two inverse transforms of a step run interleaved, sharing their exchanges (measured: no gain)
 #endif
@@ -323,20 +326,67 @@ struct Fft {
   }
 
   // in: x[a] = z[tau + T a] (folded coefficients); out: x[e] = spectrum at position 8 tau + e
+  // When the final partial pass is a single radix-2 stage (LOGM % 3 == 1, i.e. N = 2048), the two points of every
+  // butterfly sit in neighbouring lanes (stride-2 layout of the previous pass): instead of a third shared-memory
+  // exchange, lanes tau and tau^1 trade half of their points by warp shuffle and each finishes 4 butterflies.
+  static constexpr bool SHFL_LAST = TFHE_BR_SHFL_LAST && (G::REM == 1) && (G::NFULL >= 1);
+  __device__ __forceinline__ void swap_with_neighbour(double2 (&x)[8]) const {
+    const bool u = tau & 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const double sx = u ? x[k].x : x[k + 4].x, sy = u ? x[k].y : x[k + 4].y;
+      const double rx = __shfl_xor_sync(0xffffffffu, sx, 1), ry = __shfl_xor_sync(0xffffffffu, sy, 1);
+      x[k].x = u ? rx : x[k].x; x[k].y = u ? ry : x[k].y;
+      x[k + 4].x = u ? x[k + 4].x : rx; x[k + 4].y = u ? x[k + 4].y : ry;
+    }
+  }
+  // in: x[a] = point at (tau/2)*16 + tau%2 + 2a (layout of the last full pass); out: x[e] = point at 8 tau + e
+  __device__ __forceinline__ void last_stage_fwd(double2 (&x)[8]) const {
+    swap_with_neighbour(x);  // now (x[k], x[k+4]) = (even, odd) point of butterfly 4 tau + k
+    bf_fwd(x[0], x[4], tl2.x, tl2.y);
+    bf_fwd(x[1], x[5], tl2.y, -tl2.x);
+    bf_fwd(x[2], x[6], tl3.x, tl3.y);
+    bf_fwd(x[3], x[7], tl3.y, -tl3.x);
+    const double2 y1 = x[4], y2 = x[1], y3 = x[5], y4 = x[2], y5 = x[6], y6 = x[3];  // to natural order e = 2k + {0,1}
+    x[1] = y1; x[2] = y2; x[3] = y3; x[4] = y4; x[5] = y5; x[6] = y6;
+  }
+  __device__ __forceinline__ void last_stage_inv(double2 (&x)[8]) const {
+    const double2 y1 = x[1], y2 = x[2], y3 = x[3], y4 = x[4], y5 = x[5], y6 = x[6];
+    x[4] = y1; x[1] = y2; x[5] = y3; x[2] = y4; x[6] = y5; x[3] = y6;
+    bf_inv(x[0], x[4], tl2.x, tl2.y);
+    bf_inv(x[1], x[5], tl2.y, -tl2.x);
+    bf_inv(x[2], x[6], tl3.x, tl3.y);
+    bf_inv(x[3], x[7], tl3.y, -tl3.x);
+    swap_with_neighbour(x);
+  }
+
   template <class Hook>
   __device__ __forceinline__ void forward(double2 (&x)[8], const Tw4& tw0, const Hook& hook) {
     fwd_pass<0>(x, tw0);
     if constexpr (G::NPASS > 1) { exchange<0, 1>(x, hook); fwd_pass<1>(x, tw0); }
     if constexpr (G::NPASS > 2) { exchange<1, 2>(x); fwd_pass<2>(x, tw0); }
-    if constexpr (G::NPASS > 3) { exchange<2, 3>(x); fwd_pass<3>(x, tw0); }
+    if constexpr (G::NPASS > 3) {
+      if constexpr (SHFL_LAST) last_stage_fwd(x);
+      else { exchange<2, 3>(x); fwd_pass<3>(x, tw0); }
+    }
   }
   __device__ __forceinline__ void forward(double2 (&x)[8], const Tw4& tw0) { forward(x, tw0, NoHook()); }
+  // forward() split in two so that a caller can put long-latency loads in flight before the last register pass
+  __device__ __forceinline__ void forward_head(double2 (&x)[8], const Tw4& tw0) {
+    fwd_pass<0>(x, tw0);
+    if constexpr (G::NPASS > 2) { exchange<0, 1>(x); fwd_pass<1>(x, tw0); }
+    if constexpr (G::NPASS > 3) { exchange<1, 2>(x); fwd_pass<2>(x, tw0); }
+    if constexpr (G::NPASS > 1) exchange<G::NPASS - 2, G::NPASS - 1>(x);
+  }
+  __device__ __forceinline__ void forward_tail(double2 (&x)[8], const Tw4& tw0) {
+    if constexpr (G::NPASS > 1) fwd_pass<G::NPASS - 1>(x, tw0);
+  }
   // exact inverse of forward() up to the factor M (folded into the bootstrapping key); hook after the FIRST barrier
   template <class Hook>
   __device__ __forceinline__ void inverse(double2 (&x)[8], const Tw4& tw0, const Hook& hook) {
     if constexpr (G::NPASS > 3) {
-      inv_pass<3>(x, tw0); exchange<3, 2>(x, hook);
-      inv_pass<2>(x, tw0); exchange<2, 1>(x);
+      if constexpr (SHFL_LAST) { last_stage_inv(x); inv_pass<2>(x, tw0); exchange<2, 1>(x, hook); }
+      else { inv_pass<3>(x, tw0); exchange<3, 2>(x, hook); inv_pass<2>(x, tw0); exchange<2, 1>(x); }
       inv_pass<1>(x, tw0); exchange<1, 0>(x);
     } else if constexpr (G::NPASS > 2) {
       inv_pass<2>(x, tw0); exchange<2, 1>(x, hook);

@@ -20,6 +20,9 @@
 
 #include "blind_rotate.cuh"
 
+#ifndef TFHE_TM_EARLY_BK
+#define TFHE_TM_EARLY_BK 0
+#endif
 #ifndef TFHE_TM_BK_SPLIT
 #define TFHE_TM_BK_SPLIT 0
 #endif
@@ -472,10 +475,48 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
           x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
           x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
         }
-        fft.forward(x, A.tw0);
         const double2* __restrict__ rowA = bk + (size_t)(r * 2 + 0) * M;
         const double2* __restrict__ rowB = rowA + M;
-#if TFHE_TM_BK_SPLIT
+#if TFHE_TM_EARLY_BK
+        // all 16 key values requested BEFORE the last register pass: the L2 latency hides behind 72 FMAs
+        fft.forward_head(x, A.tw0);
+        double2 ka[8], kb[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { ka[e] = __ldg(rowA + e * T); kb[e] = __ldg(rowB + e * T); }
+        uint32_t ra0[16], rb0[16];
+        if (r > 0) { tmem_ld16(tacc, ra0); tmem_ld16(tacc + 32, rb0); }
+        fft.forward_tail(x, A.tw0);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          double2 aA[4], aB[4];
+          uint32_t ra[16], rb[16];
+          if (r > 0) {
+            if (h == 1) { tmem_ld16(tacc + 16, ra); tmem_ld16(tacc + 48, rb); }
+            tmem_wait_ld();
+            if (h == 0) { unpack4(ra0, aA); unpack4(rb0, aB); } else { unpack4(ra, aA); unpack4(rb, aB); }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { aA[q] = make_double2(0.0, 0.0); aB[q] = make_double2(0.0, 0.0); }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int e = 4 * h + q;
+            aA[q].x = fma(x[e].x, ka[e].x, aA[q].x);
+            aA[q].x = fma(-x[e].y, ka[e].y, aA[q].x);
+            aA[q].y = fma(x[e].x, ka[e].y, aA[q].y);
+            aA[q].y = fma(x[e].y, ka[e].x, aA[q].y);
+            aB[q].x = fma(x[e].x, kb[e].x, aB[q].x);
+            aB[q].x = fma(-x[e].y, kb[e].y, aB[q].x);
+            aB[q].y = fma(x[e].x, kb[e].y, aB[q].y);
+            aB[q].y = fma(x[e].y, kb[e].x, aB[q].y);
+          }
+          pack4(aA, ra);
+          pack4(aB, rb);
+          tmem_st16(tacc + 16 * h, ra);
+          tmem_st16(tacc + 32 + 16 * h, rb);
+        }
+#elif TFHE_TM_BK_SPLIT
+        fft.forward(x, A.tw0);
         // key values and accumulator columns one half (4 points) at a time, next half in flight: 32 + 32 registers
         double2 ka[2][4], kb[2][4];
 #pragma unroll
@@ -516,6 +557,7 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
           tmem_st16(tacc + 32 + 16 * h, rb);
         }
 #else
+        fft.forward(x, A.tw0);
         double2 ka[8], kb[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) { ka[e] = __ldg(rowA + e * T); kb[e] = __ldg(rowB + e * T); }  // all 16 in flight
