@@ -137,3 +137,26 @@ def test_circuit_builder_bookkeeping(T):
     m = T.circuit.Circuit(3)
     m.outputs([m.gate("MUX", 0, 1, 2)])
     assert m.n_bootstraps == 3 and m.n_levels == 2
+
+
+def test_wire_format_round_trip_and_rejects_corruption(T):
+    P = T.params.get("80")
+    sk = T.key.NewSecretKey(P, 3)
+    ck = T.cloudkey.NewCloudKey(sk, 4)
+    sk2 = T.wire.loads_secret_key(T.wire.dumps_secret_key(sk), P)
+    assert np.array_equal(sk2.KeyLv0, sk.KeyLv0) and np.array_equal(sk2.KeyLv1, sk.KeyLv1)
+    blob = T.wire.dumps_cloud_key(ck)
+    ck2 = T.wire.loads_cloud_key(blob, P)
+    assert ck2.DecompositionOffset == ck.DecompositionOffset
+    assert np.array_equal(ck2.BootstrappingKey, ck.BootstrappingKey) and np.array_equal(ck2.KeySwitchingKey, ck.KeySwitchingKey)
+    assert np.array_equal(ck2.BlindRotateTestvec, ck.BlindRotateTestvec)
+    ct = T.tlwe.EncryptBool([1, 0, 1], sk, 5)
+    assert np.array_equal(T.wire.loads_ciphertexts(T.wire.dumps_ciphertexts(P, ct), P), ct)
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 1
+    with pytest.raises(ValueError):
+        T.wire.loads_cloud_key(bytes(bad), P)
+    with pytest.raises(ValueError):
+        T.wire.loads_cloud_key(blob, T.params.get("128"))
+    with pytest.raises(ValueError):
+        T.wire.loads_secret_key(blob, P)
