@@ -30,6 +30,9 @@
 #ifndef TFHE_BR_KEEP_OWN
 #define TFHE_BR_KEEP_OWN 0      // 1: exchanges keep the one point that does not change owner in its register (measured 3.5% slower: the predicated asm blocks pin the schedule)
 #endif
+#ifndef TFHE_BR_TL_RELOAD
+#define TFHE_BR_TL_RELOAD 0     // 1: last-pass twiddles re-read from L1 every transform (frees 16 registers)
+#endif
 #ifndef TFHE_BR_SHFL_LAST
 #define TFHE_BR_SHFL_LAST 1     // N = 2048: last radix-2 stage through a lane-pair shuffle instead of a third exchange
 #endif
@@ -304,8 +307,12 @@ struct Fft {
   __device__ __forceinline__ void fwd_pass(double2 (&x)[8], const Tw4& tw0) {
     if constexpr (K == 0) {
       radix8_fwd<3>(x, tw0.s[0], tw0.s[1], tw0.s[2], tw0.s[3]);
-    } else if constexpr (K == G::NPASS - 1) {
+    } else if constexpr (K == G::NPASS - 1 && !TFHE_BR_TL_RELOAD) {
       radix8_fwd<G::nstages(K)>(x, tl0, tl1, tl2, tl3);
+    } else if constexpr (K == G::NPASS - 1) {  // last-pass twiddles re-read from L1 instead of living in 16 registers
+      const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
+      double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
+      radix8_fwd<G::nstages(K)>(x, s0, s1, s2, s3);
     } else {
       const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
       double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
@@ -316,8 +323,12 @@ struct Fft {
   __device__ __forceinline__ void inv_pass(double2 (&x)[8], const Tw4& tw0) {
     if constexpr (K == 0) {
       radix8_inv<3>(x, tw0.s[0], tw0.s[1], tw0.s[2], tw0.s[3]);
-    } else if constexpr (K == G::NPASS - 1) {
+    } else if constexpr (K == G::NPASS - 1 && !TFHE_BR_TL_RELOAD) {
       radix8_inv<G::nstages(K)>(x, tl0, tl1, tl2, tl3);
+    } else if constexpr (K == G::NPASS - 1) {
+      const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
+      double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
+      radix8_inv<G::nstages(K)>(x, s0, s1, s2, s3);
     } else {
       const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
       double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
@@ -559,8 +570,15 @@ constexpr size_t br_smem_bytes(int n) {
 // ---------------------------------------------------------------------------------------------
 // The kernel: grid = count gates, block = T = N/16 threads.
 // ---------------------------------------------------------------------------------------------
+// TFHE_BR_LB_THREADS / TFHE_BR_LB_BLOCKS: experiment knob — declare looser launch bounds than the real block size to
+// steer ptxas to a register budget between the (64,4) -> 255 and (64,5) -> 168 choices, e.g. (160,2) -> ~200.
+#ifdef TFHE_BR_LB_THREADS
+#define TFHE_BR_BOUNDS(T, MINB) __launch_bounds__(TFHE_BR_LB_THREADS, TFHE_BR_LB_BLOCKS)
+#else
+#define TFHE_BR_BOUNDS(T, MINB) __launch_bounds__(T, MINB)
+#endif
 template <int LOGN, int L, int BGBIT, bool SMALL, int MINB, bool TEX = false>
-__global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_kernel(const BrArgs A) {
+__global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(const BrArgs A) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]

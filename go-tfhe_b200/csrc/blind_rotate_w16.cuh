@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(128, MINB) blind_rotate_w16_kernel(const BrW16
 // registers, i.e. from 4 to 6 resident blocks per SM, to overlap the shared-memory and FP64 pipes better.
 // =============================================================================================
 template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
-__global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_tm_kernel(const BrArgs A) {
+__global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kernel(const BrArgs A) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
   static_assert(T >= 32 && T <= 128, "one TMEM lane per thread");
   constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);

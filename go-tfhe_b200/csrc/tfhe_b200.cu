@@ -18,6 +18,7 @@
 
 #include "blind_rotate.cuh"
 #include "blind_rotate_w16.cuh"
+#include "blind_rotate_tx.cuh"
 #include "lwe_kernels.cuh"
 
 using namespace tfhe;
@@ -143,6 +144,8 @@ struct Variant {
   size_t (*br_staged_smem)(int n);
   void (*br_w16)(const BrW16Args);   // warp-per-gate, TMEM accumulators (N = 1024 only, else nullptr)
   void (*br_tm)(const BrArgs);       // block-per-gate, TMEM accumulators (N >= 1024, else nullptr)
+  void (*br_tx)(const BrArgs);       // block-per-gate, second transform exchange through TMEM (N = 1024, else nullptr)
+  void (*br_txs)(const BrArgs);      // same + key rows TMA-staged through shared memory
 };
 template <int LOGN> size_t br_smem(int n) { return br_smem_bytes<LOGN>(n); }
 template <int LOGN> size_t br_staged_smem(int n) { return br_staged_smem_bytes<LOGN>(n); }
@@ -152,6 +155,19 @@ template <int LOGN> size_t br_staged_smem(int n) { return br_staged_smem_bytes<L
 template <int LOGN, int L, int BG, bool SMALL>
 constexpr auto w16_kernel() -> void (*)(const BrW16Args) {
   if constexpr (LOGN == 10) return blind_rotate_w16_kernel<L, BG, SMALL, TFHE_BR_W16_MINB>;
+  else return nullptr;
+}
+#ifndef TFHE_BR_TX_MINB
+#define TFHE_BR_TX_MINB 4
+#endif
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto tx_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10) return blind_rotate_tx_kernel<L, BG, SMALL, TFHE_BR_TX_MINB>;
+  else return nullptr;
+}
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto txs_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10) return blind_rotate_txs_kernel<L, BG, SMALL, TFHE_BR_TX_MINB>;
   else return nullptr;
 }
 #ifndef TFHE_BR_TM_MINB_N1024
@@ -170,7 +186,8 @@ constexpr auto tm_kernel() -> void (*)(const BrArgs) {
   { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>,                              \
     blind_rotate_kernel<LOGN, L, BG, SMALL, MINB, true>,                                            \
     blind_rotate_staged_kernel<LOGN, L, BG, SMALL, MINBS>, cmux_kernel<LOGN, L, BG, SMALL, MINB>,   \
-    br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>() }
+    br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>(),           \
+    tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>() }
 #ifndef TFHE_BR_MINB_N1024
 #define TFHE_BR_MINB_N1024 4
 #endif
@@ -218,10 +235,17 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
     return 0;
   }
   a.bsk_tex = c->bsk_tex;
-  if (c->br_variant == 4 && V.br_tm) V.br_tm<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  if (c->br_variant == 6 && V.br_txs) V.br_txs<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
+  else if (c->br_variant == 5 && V.br_tx) V.br_tx<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  else if (c->br_variant == 4 && V.br_tm) V.br_tm<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 1) V.br_staged<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 2) V.br_tex<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
-  else V.br<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  else {
+    size_t extra = 0;  // experiment knob: TFHE_B200_EXTRA_SMEM=<bytes> lowers occupancy of the default kernel
+    if (const char* e = getenv("TFHE_B200_EXTRA_SMEM")) extra = (size_t)atol(e);
+    if (extra) cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V.br_smem(4096) + extra));
+    V.br<<<(unsigned)count, T, V.br_smem(c->P.n) + extra, s>>>(a);
+  }
   c->launches++;
   CK(c, cudaGetLastError());
   return 0;
@@ -325,6 +349,10 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   const Variant& V = kVariants[v];
   if (V.br_tm && (e = cudaFuncSetAttribute(V.br_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tm)", e);
+  if (V.br_tx && (e = cudaFuncSetAttribute(V.br_tx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_tx)", e);
+  if (V.br_txs && (e = cudaFuncSetAttribute(V.br_txs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_staged_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_txs)", e);
   if (V.br_w16) {
     const int M = 512;
     auto blk = [&](int m, int i, double2* o) {
@@ -354,7 +382,7 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
   if (const char* sel = getenv("TFHE_B200_BR"))
-    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
   if ((e = cudaFuncSetAttribute(key_switch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -783,7 +811,8 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) { return c ? c->launches : 0
 
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;
-  if (variant < 0 || variant > 4) return fail(c, TFHE_ERR_ARG, "variant must be 0 (ldg), 1 (tma), 2 (tex), 3 (w16) or 4 (tmem)");
+  if (variant < 0 || variant > 6) return fail(c, TFHE_ERR_ARG, "variant must be 0 (ldg), 1 (tma), 2 (tex), 3 (w16), 4 (tmem), 5 (tmex) or 6 (tmex+tma)");
+  if (variant >= 5 && !kVariants[c->variant].br_tx) return fail(c, TFHE_ERR_ARG, "the TMEM-exchange kernel exists for N = 1024 only");
   if (variant == 4 && !kVariants[c->variant].br_tm) return fail(c, TFHE_ERR_ARG, "the TMEM-accumulator kernel needs N >= 1024");
   if (variant == 3 && !kVariants[c->variant].br_w16) return fail(c, TFHE_ERR_ARG, "the warp-per-gate kernel exists for N = 1024 only");
   if (variant == 2 && c->key_loaded && !c->bsk_tex) return fail(c, TFHE_ERR_STATE, "no texture object");

@@ -154,8 +154,9 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
 /* Selects the blind-rotate kernel: 0 = block per gate, key rows by LDG straight from L2 (default), 1 = key rows
  * TMA-staged through shared memory (cp.async.bulk + mbarrier), 2 = key rows through the texture pipe, 3 = one warp
  * per gate with 16 points per thread and the spectrum accumulators in tensor memory (N = 1024 only), 4 = block per
- * gate with the accumulators in tensor memory (N >= 1024).  All compute identical results; the default is the
- * fastest measured (profiles/r01_experiments.md). */
+ * gate with the accumulators in tensor memory (N >= 1024), 5 = block per gate with the second transform exchange
+ * through tensor memory + a lane shuffle (N = 1024), 6 = 5 plus TMA-staged key rows.  All compute identical results;
+ * the default is the fastest measured (profiles/r01_experiments.md). */
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
 /* Per-stage device timing for bench.py's roofline: when enabled, every bootstrap batch records CUDA events on
  * its launching stream around the blind-rotate kernel and the key-switch kernel.  tfhe_ctx_collect_timing waits

@@ -84,6 +84,10 @@ def test_key_fetch_variants_agree(O, gpu, name):
         if P.N == 1024:  # warp-per-gate kernel with TMEM accumulators: a different transform schedule, same exact result
             ctx.set_blind_rotate_variant("w16")
             outs["w16"] = ctx.blind_rotate_batch(ct)
+            ctx.set_blind_rotate_variant("tmex")  # block per gate, second exchange through TMEM + lane shuffle
+            outs["tmex"] = ctx.blind_rotate_batch(ct)
+            ctx.set_blind_rotate_variant("tmex+tma")
+            outs["tmex+tma"] = ctx.blind_rotate_batch(ct)
         ctx.set_blind_rotate_variant("tmem")  # block-per-gate kernel with the accumulators in TMEM
         outs["tmem"] = ctx.blind_rotate_batch(ct)
     finally:
@@ -91,6 +95,7 @@ def test_key_fetch_variants_agree(O, gpu, name):
     assert np.array_equal(outs["ldg"], outs["tma"]) and np.array_equal(outs["ldg"], outs["tex"])
     if "w16" in outs:
         assert np.array_equal(outs["ldg"], outs["w16"])
+        assert np.array_equal(outs["ldg"], outs["tmex"]) and np.array_equal(outs["ldg"], outs["tmex+tma"])
     assert np.array_equal(outs["ldg"], outs["tmem"])
     if name == "80":
         ev = O.Evaluator(P.N)
