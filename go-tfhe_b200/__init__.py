@@ -7,9 +7,9 @@ params, key, tlwe, lut, cloudkey, evaluator, gates.  All hot-path compute runs i
 
 The directory name contains a hyphen; import it with importlib.import_module("go-tfhe_b200").
 """
-from . import _native, params, engine, key, tlwe, lut, cloudkey, evaluator, gates, sharding, circuit, wire  # noqa: F401
+from . import _native, params, engine, key, tlwe, lut, poly, cloudkey, evaluator, gates, sharding, circuit, wire  # noqa: F401
 from .build import build  # noqa: F401
 from .engine import Context, TfheError, OPCODES  # noqa: F401
 
-__all__ = ["params", "engine", "key", "tlwe", "lut", "cloudkey", "evaluator", "gates", "sharding", "circuit", "wire", "build", "Context",
+__all__ = ["params", "engine", "key", "tlwe", "lut", "poly", "cloudkey", "evaluator", "gates", "sharding", "circuit", "wire", "build", "Context",
            "TfheError", "OPCODES"]

@@ -776,6 +776,88 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_staged_k
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stand-alone polynomial transforms in the REFERENCE's FourierPoly layout (groups of 4 real + 4 imaginary parts,
+// poly/poly.go:54-62), one block per polynomial — rows a11, a13, a22 of SURVEY.md section 8 at API granularity:
+//   mode 0  Evaluator.ToFourierPolyAssign   poly/fourier_transform.go:18-21   u32[N]  -> f64[N]
+//   mode 1  Evaluator.ToPolyAssign          poly/fourier_transform.go:31-44   f64[N]  -> u32[N]  (divide by N/2, mod 2^32)
+//   mode 2  Evaluator.MulPolyAssign         poly/poly_mul.go:12-22            u32[N] x u32[N] -> u32[N]
+// ---------------------------------------------------------------------------------------------
+struct PolyArgs {
+  const void* in0;
+  const void* in1;
+  void* out;
+  const double2* tw_tab;
+  int mode;
+  Tw4 tw0;
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__((1 << (LOGN - 4)), 2) poly_kernel(const PolyArgs A) {
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double2* ex = reinterpret_cast<double2*>(smem_raw);  // [2][EXW][M]
+  const int tau = threadIdx.x;
+  const size_t g = blockIdx.x;
+  Fft<LOGN - 1, false> fft;
+  fft.init(ex, A.tw_tab, tau);
+  __syncthreads();
+  auto load_folded = [&](const uint32_t* p, double2 (&x)[8]) {  // fourier_transform.go:64-85
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      x[a].x = (double)(int32_t)p[j];
+      x[a].y = (double)(int32_t)p[j + M];
+    }
+  };
+  auto store_poly = [&](const double2 (&x)[8], uint32_t* p) {  // fourier_transform.go:88-125
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      p[j] = to_torus<false>(x[a].x);
+      p[j + M] = to_torus<false>(x[a].y);
+    }
+  };
+  const double inv_m = 1.0 / (double)M;
+  if (A.mode == 0) {
+    double2 x[8];
+    load_folded(reinterpret_cast<const uint32_t*>(A.in0) + g * N, x);
+    fft.forward(x, A.tw0);
+    double* o = reinterpret_cast<double*>(A.out) + g * N;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int k = 8 * tau + e;
+      o[(k >> 2) * 8 + (k & 3)] = x[e].x;
+      o[(k >> 2) * 8 + 4 + (k & 3)] = x[e].y;
+    }
+  } else if (A.mode == 1) {
+    double2 x[8];
+    const double* in = reinterpret_cast<const double*>(A.in0) + g * N;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int k = 8 * tau + e;
+      x[e].x = in[(k >> 2) * 8 + (k & 3)] * inv_m;
+      x[e].y = in[(k >> 2) * 8 + 4 + (k & 3)] * inv_m;
+    }
+    fft.inverse(x, A.tw0);
+    store_poly(x, reinterpret_cast<uint32_t*>(A.out) + g * N);
+  } else {
+    double2 x[8], y[8];
+    load_folded(reinterpret_cast<const uint32_t*>(A.in0) + g * N, x);
+    fft.forward(x, A.tw0);
+    load_folded(reinterpret_cast<const uint32_t*>(A.in1) + g * N, y);
+    fft.forward(y, A.tw0);
+#pragma unroll
+    for (int e = 0; e < 8; e++) {  // poly/fourier_ops.go:138-161, scaled by 1/M for the inverse
+      const double re = (x[e].x * y[e].x - x[e].y * y[e].y) * inv_m;
+      const double im = (x[e].x * y[e].y + x[e].y * y[e].x) * inv_m;
+      x[e] = make_double2(re, im);
+    }
+    fft.inverse(x, A.tw0);
+    store_poly(x, reinterpret_cast<uint32_t*>(A.out) + g * N);
+  }
+}
+
 // Single CMUX / external product on global-memory TRLWEs (parity-test granularity; rows a9, a14).
 template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
 __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const CmuxArgs A) {

@@ -708,6 +708,8 @@ int tfhe_key_switch_batch(tfhe_ctx* c, int64_t count, const uint32_t* lwe_in, ui
 }
 
 
+static int h2d(tfhe_ctx* c, DevBuf& b, const void* src, size_t bytes);
+
 // ---- levelised circuit runner --------------------------------------------------------------------------
 int tfhe_circuit_run(tfhe_ctx* c, int64_t instances, int32_t n_inputs, int32_t n_gates, const tfhe_gate_desc* gates,
                      const uint32_t* inputs, int32_t n_outputs, const int32_t* output_wires, uint32_t* outputs) {
@@ -805,6 +807,46 @@ int tfhe_circuit_run(tfhe_ctx* c, int64_t instances, int32_t n_inputs, int32_t n
                           cudaMemcpyDeviceToHost, s));
   CK(c, cudaStreamSynchronize(s));
   return TFHE_OK;
+}
+
+// ---- stand-alone polynomial transforms (reference FourierPoly layout) --------------------------------------
+static int poly_call(tfhe_ctx* c, int mode, int64_t count, const void* in0, size_t in0_bytes, const void* in1,
+                     size_t in1_bytes, void* out, size_t out_bytes) {
+  if (!c) return TFHE_ERR_ARG;
+  if (count < 0 || (count > 0 && (!in0 || !out || (mode == 2 && !in1)))) return fail(c, TFHE_ERR_ARG, "bad polynomial batch arguments");
+  if (count == 0) return TFHE_OK;
+  int rc = set_device(c);
+  if (rc) return rc;
+  if ((rc = h2d(c, c->h2d_a, in0, in0_bytes))) return rc;
+  if (mode == 2 && (rc = h2d(c, c->h2d_b, in1, in1_bytes))) return rc;
+  CK(c, c->d2h_out.reserve(out_bytes));
+  PolyArgs a{};
+  a.in0 = c->h2d_a.p; a.in1 = c->h2d_b.p; a.out = c->d2h_out.p; a.tw_tab = c->d_tw; a.mode = mode; a.tw0 = c->tw0;
+  const int N = c->P.N, T = N / 16;
+  const size_t sm = (size_t)2 * TFHE_BR_EXW * (N / 2) * 16;
+  switch (c->logN) {
+    case 9: poly_kernel<9><<<(unsigned)count, T, sm, c->stream>>>(a); break;
+    case 10: poly_kernel<10><<<(unsigned)count, T, sm, c->stream>>>(a); break;
+    default: poly_kernel<11><<<(unsigned)count, T, sm, c->stream>>>(a); break;
+  }
+  c->launches++;
+  CK(c, cudaGetLastError());
+  CK(c, cudaMemcpyAsync(out, c->d2h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+int tfhe_to_fourier_batch(tfhe_ctx* c, int64_t count, const uint32_t* poly_in, double* fourier_out) {
+  const size_t N = c ? (size_t)c->P.N : 0;
+  return poly_call(c, 0, count, poly_in, (size_t)count * N * 4, nullptr, 0, fourier_out, (size_t)count * N * 8);
+}
+int tfhe_to_poly_batch(tfhe_ctx* c, int64_t count, const double* fourier_in, uint32_t* poly_out) {
+  const size_t N = c ? (size_t)c->P.N : 0;
+  return poly_call(c, 1, count, fourier_in, (size_t)count * N * 8, nullptr, 0, poly_out, (size_t)count * N * 4);
+}
+int tfhe_mul_poly_batch(tfhe_ctx* c, int64_t count, const uint32_t* p0, const uint32_t* p1, uint32_t* out) {
+  const size_t N = c ? (size_t)c->P.N : 0;
+  return poly_call(c, 2, count, p0, (size_t)count * N * 4, p1, (size_t)count * N * 4, out, (size_t)count * N * 4);
 }
 
 int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) { return c ? c->launches : 0; }

@@ -136,6 +136,27 @@ class Context:
         self._ck(self.lib.tfhe_key_switch_batch(self.h, len(x), _ptr(x), _ptr(out)), "tfhe_key_switch_batch")
         return out
 
+    def to_fourier_batch(self, polys):
+        """poly.Evaluator.ToFourierPoly for a batch: [count][N] u32 -> [count][N] f64 (reference layout)."""
+        p = _u32(polys, (-1, self.P.N))
+        out = np.empty(p.shape, dtype=np.float64)
+        self._ck(self.lib.tfhe_to_fourier_batch(self.h, len(p), _ptr(p), _ptr(out)), "tfhe_to_fourier_batch")
+        return out
+
+    def to_poly_batch(self, fps):
+        """poly.Evaluator.ToPoly for a batch: [count][N] f64 (reference layout) -> [count][N] u32."""
+        f = np.ascontiguousarray(fps, dtype=np.float64).reshape(-1, self.P.N)
+        out = np.empty(f.shape, dtype=np.uint32)
+        self._ck(self.lib.tfhe_to_poly_batch(self.h, len(f), _ptr(f), _ptr(out)), "tfhe_to_poly_batch")
+        return out
+
+    def mul_poly_batch(self, p0, p1):
+        """poly.Evaluator.MulPoly for a batch."""
+        a, b = _u32(p0, (-1, self.P.N)), _u32(p1, (-1, self.P.N))
+        out = np.empty_like(a)
+        self._ck(self.lib.tfhe_mul_poly_batch(self.h, len(a), _ptr(a), _ptr(b), _ptr(out)), "tfhe_mul_poly_batch")
+        return out
+
     def circuit_run(self, gates, n_inputs, inputs, output_wires):
         """gates: list of (op, in0, in1, in2, out); inputs [n_inputs][instances][n+1] -> [n_outputs][instances][n+1]."""
         P = self.P

@@ -125,6 +125,17 @@ int tfhe_sample_extract_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* trlw
  * LWE [count][N+1] -> LWE [count][n+1]. */
 int tfhe_key_switch_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* lwe_in, uint32_t* ct_out);
 
+/* --- polynomial transforms at API granularity (reference FourierPoly layout in and out) ---------------------- */
+/* poly.Evaluator.ToFourierPolyAssign (poly/fourier_transform.go:18-21): [count][N] u32 -> [count][N] f64, unscaled,
+ * coefficients read as int32, output in the reference's order and 4-real/4-imaginary packing. */
+int tfhe_to_fourier_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* poly_in, double* fourier_out);
+/* poly.Evaluator.ToPolyAssign (poly/fourier_transform.go:31-44): inverse transform, divide by N/2, reduce mod 2^32
+ * with rounding, [count][N] f64 -> [count][N] u32. */
+int tfhe_to_poly_batch(tfhe_ctx* ctx, int64_t count, const double* fourier_in, uint32_t* poly_out);
+/* poly.Evaluator.MulPolyAssign (poly/poly_mul.go:12-22): negacyclic product of two torus polynomials, both read as
+ * int32 coefficients, [count][N] x [count][N] -> [count][N]. */
+int tfhe_mul_poly_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* p0, const uint32_t* p1, uint32_t* out);
+
 /* --- levelised circuits (additive: the caller immediately above the path) ------------------------------- */
 /* One gate of a circuit over wire ids.  Wires 0..n_inputs-1 are the inputs; every gate writes a distinct wire
  * >= n_inputs and may read only inputs or wires written by EARLIER gates of the list (topological order).

@@ -291,3 +291,23 @@ def test_circuit_mux_not_copy_and_errors(T, O, gpu):
         ctx.circuit_run([("AND", 0, 5, 0, 3)], 3, ins, [3])
     with pytest.raises(T.TfheError):  # writes an input wire
         ctx.circuit_run([("AND", 0, 1, 0, 2)], 3, ins, [2])
+
+
+@pytest.mark.parametrize("name", ["80", "uint2", "uint5"])
+def test_polynomial_transforms_and_mul_poly(T, O, gpu, name):  # rows a11, a13, a22
+    """ToFourierPoly / ToPoly / MulPoly at API granularity, in the reference's FourierPoly layout.
+    Forward: same evaluation points in the same order and packing, values within 1e-11 relative (different butterfly
+    rounding; stated).  Inverse of an exactly representable integer spectrum, round trip and MulPoly with a binary
+    key (the only use the reference makes of it, trlwe/trlwe.go:43): bit-exact."""
+    P, sk, ck, ctx = gpu(name)
+    ev = O.Evaluator(P.N)
+    rng = np.random.default_rng(13)
+    polys = rng.integers(0, 1 << 32, (4, P.N), dtype=np.uint64).astype(np.uint32)
+    fp = ctx.to_fourier_batch(polys)
+    want = np.stack([ev.to_fourier(p) for p in polys])
+    assert np.max(np.abs(fp - want)) <= 1e-11 * np.max(np.abs(want))
+    back = ctx.to_poly_batch(want)                 # oracle spectrum -> GPU inverse
+    assert np.array_equal(back, polys)
+    assert np.array_equal(ctx.to_poly_batch(fp), polys)   # GPU round trip (poly/poly_test.go:10-33 allows 10 LSB; exact here)
+    keys = np.stack([sk.s1] * 4)
+    assert np.array_equal(ctx.mul_poly_batch(polys, keys), np.stack([ev.mul_poly(p, sk.s1) for p in polys]))
