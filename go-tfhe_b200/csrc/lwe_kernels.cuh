@@ -59,9 +59,8 @@ __global__ void gate_prepare_kernel(long long count, const uint8_t* __restrict__
   }
 }
 
-// Second level of MUX: out = OR(x, y) prologue = x + y + 1/8, for gates whose op is MUX.
-__global__ void mux_or_prepare_kernel(long long count, const uint8_t* __restrict__ ops, long long nops,
-                                      const uint32_t* __restrict__ x, const uint32_t* __restrict__ y,
+// Second level of MUX: out = OR(x, y) prologue = x + y + 1/8, one block per MUX gate.
+__global__ void mux_or_prepare_kernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ y,
                                       uint32_t* __restrict__ out, int n) {
   const long long g = blockIdx.x;
   const size_t row = (size_t)g * (n + 1);

@@ -64,7 +64,7 @@ struct tfhe_ctx {
   cudaStream_t stream = nullptr;  // used by the host-buffer API
   DevBuf prep, lwe1, tmp, prep2, idx_a, idx_b, ops_dev;       // engine scratch
   DevBuf wires, gate_descs;                                   // circuit runner
-  DevBuf h2d_a, h2d_b, h2d_c, h2d_luts, d2h_out, key_stage;   // staging for the host-buffer API
+  DevBuf h2d_a, h2d_b, h2d_c, h2d_luts, d2h_out;              // staging for the host-buffer API
   int64_t launches = 0;
   int sm_count = 0;
   std::string err;
@@ -240,12 +240,7 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   else if (c->br_variant == 4 && V.br_tm) V.br_tm<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 1) V.br_staged<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 2) V.br_tex<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
-  else {
-    size_t extra = 0;  // experiment knob: TFHE_B200_EXTRA_SMEM=<bytes> lowers occupancy of the default kernel
-    if (const char* e = getenv("TFHE_B200_EXTRA_SMEM")) extra = (size_t)atol(e);
-    if (extra) cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(V.br_smem(4096) + extra));
-    V.br<<<(unsigned)count, T, V.br_smem(c->P.n) + extra, s>>>(a);
-  }
+  else V.br<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   c->launches++;
   CK(c, cudaGetLastError());
   return 0;
@@ -397,7 +392,7 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   for (DevBuf* b : {&c->wires, &c->gate_descs, &c->prep, &c->lwe1, &c->tmp, &c->prep2, &c->idx_a, &c->idx_b, &c->ops_dev, &c->h2d_a, &c->h2d_b,
-                    &c->h2d_c, &c->h2d_luts, &c->d2h_out, &c->key_stage})
+                    &c->h2d_c, &c->h2d_luts, &c->d2h_out})
     b->release();
   for (auto* v : {&c->ev_live, &c->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); cudaEventDestroy(ev.e2); }
@@ -566,8 +561,7 @@ int tfhe_gate_batch_device(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64
   }
   if (nm) {  // level 2: OR(andAB, andNotAC)
     uint32_t* in2 = in1;  // reuse
-    mux_or_prepare_kernel<<<(unsigned)nm, 256, 0, s>>>(nm, nullptr, 0, out1 + (size_t)nb * n1, out1 + (size_t)(nb + nm) * n1,
-                                                       in2, c->P.n);
+    mux_or_prepare_kernel<<<(unsigned)nm, 256, 0, s>>>(out1 + (size_t)nb * n1, out1 + (size_t)(nb + nm) * n1, in2, c->P.n);
     c->launches++;
     CK(c, cudaGetLastError());
     uint32_t* out2 = out1;  // level-1 outputs are consumed by now (stream order)
