@@ -33,7 +33,7 @@ def _nvcc():
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     inc = os.path.join(os.path.dirname(HERE), "include")
-    eng_src = [os.path.join(CSRC, f) for f in ("tfhe_b200.cu", "blind_rotate.cuh", "lwe_kernels.cuh")] + \
+    eng_src = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
               [os.path.join(inc, "tfhe_b200.h")]
     if force or _stale(ENGINE, eng_src):
         cmd = [_nvcc()] + NVCC_FLAGS + ["-o", ENGINE, os.path.join(CSRC, "tfhe_b200.cu")]

@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 // Build-time tuning knobs (defaults are the measured best; see profiles/).
 #ifndef TFHE_BR_UNROLL_POLY
@@ -41,6 +42,12 @@
 #endif
 #ifndef TFHE_BR_PAIR_FWD
 #define TFHE_BR_PAIR_FWD 0      // forward transforms of consecutive decomposition levels run interleaved in pairs
+#endif
+#ifndef TFHE_BR_KPIPE
+#define TFHE_BR_KPIPE 1         // 1: key rows are software-pipelined in registers: the 16 loads of digit r+1 are issued right after the MAC of digit r (across the loop back-edge and into the next step)
+#endif
+#ifndef TFHE_BR_PF_L1
+#define TFHE_BR_PF_L1 0         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread)
 #endif
 // exchange buffers hold one transform ([2][M]) unless a paired mode needs two ([2][2M])
 #define TFHE_BR_EXW ((TFHE_BR_PAIR_INV || TFHE_BR_PAIR_FWD) ? 2 : 1)
@@ -470,9 +477,12 @@ struct KeyTex {
   }
 };
 
-template <int LOGN, int L, int BGBIT, bool SMALL, class Key>
+// KP = true (LDG policy only): kA/kB hold the rows of the first digit on entry and the first digit of the NEXT row-set
+// (bk + one step) on exit; every MAC is followed at once by the loads of the digit after it.
+template <int LOGN, int L, int BGBIT, bool SMALL, bool KP, class Key>
 __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, false>& fft, const Key bk,
-                                                 int at, uint32_t offset, const Tw4& tw0) {
+                                                 int at, uint32_t offset, const Tw4& tw0, double2 (&kA)[8],
+                                                 double2 (&kB)[8]) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
   constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
   constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
@@ -485,10 +495,18 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
   auto mac = [&](const double2 (&x)[8], int r) {
     const int rowA = (r * 2 + 0) * M + tau;
     const int rowB = rowA + M;
+#if TFHE_BR_PF_L1
+    if constexpr (!std::is_same<Key, KeyTex>::value) {  // rows of digit r + d (contiguous into the next step's row-set)
+      const char* pf = reinterpret_cast<const char*>(bk.p + (r + TFHE_BR_PF_L1) * 2 * M) + tau * 128;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
+    }
+#endif
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const double2 ka = bk(rowA + e * T);
-      const double2 kb = bk(rowB + e * T);
+      double2 ka, kb;
+      if constexpr (KP) { ka = kA[e]; kb = kB[e]; }
+      else { ka = bk(rowA + e * T); kb = bk(rowB + e * T); }
       accA[e].x = fma(x[e].x, ka.x, accA[e].x);
       accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
       accA[e].y = fma(x[e].x, ka.y, accA[e].y);
@@ -497,6 +515,13 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
       accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
       accB[e].y = fma(x[e].x, kb.y, accB[e].y);
       accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+    }
+    if constexpr (KP) {  // rows of digit r + 1 (row-sets are contiguous: after the last digit this is the next step)
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        kA[e] = bk(rowA + 2 * M + e * T);
+        kB[e] = bk(rowB + 2 * M + e * T);
+      }
     }
   };
 
@@ -607,13 +632,23 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
   __syncthreads();
 
   const size_t row_stride = (size_t)2 * L * 2 * M;
+  double2 kA[8], kB[8];
+  int pref = -1;  // step whose first-digit rows are already in kA/kB
   for (int i = 0; i < n; i++) {
     const int at = abar[i];
     if (at == 0) continue;  // X^0: ct1 - ct0 = 0, digits are all zero, the step is an exact no-op
     if constexpr (TEX)
-      cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyTex{A.bsk_tex, (int)(row_stride * i)}, at, A.offset, A.tw0);
-    else
-      cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyLdg{A.bsk + row_stride * i}, at, A.offset, A.tw0);
+      cmux_rotate_step<LOGN, L, BGBIT, SMALL, false>(acc, fft, KeyTex{A.bsk_tex, (int)(row_stride * i)}, at, A.offset, A.tw0, kA, kB);
+    else if constexpr (TFHE_BR_KPIPE) {
+      const KeyLdg bk{A.bsk + row_stride * i};
+      if (pref != i) {  // first step, or the one after a skipped step
+#pragma unroll
+        for (int e = 0; e < 8; e++) { kA[e] = bk(tau + e * T); kB[e] = bk(M + tau + e * T); }
+      }
+      cmux_rotate_step<LOGN, L, BGBIT, SMALL, true>(acc, fft, bk, at, A.offset, A.tw0, kA, kB);
+      pref = i + 1;  // the last MAC loaded the first rows of step i + 1 (the key buffer has slack past step n - 1)
+    } else
+      cmux_rotate_step<LOGN, L, BGBIT, SMALL, false>(acc, fft, KeyLdg{A.bsk + row_stride * i}, at, A.offset, A.tw0, kA, kB);
     __syncthreads();
   }
 

@@ -20,6 +20,7 @@
 #include "blind_rotate_w16.cuh"
 #include "blind_rotate_tx.cuh"
 #include "lwe_kernels.cuh"
+#include "key_switch_mma.cuh"
 
 using namespace tfhe;
 
@@ -60,6 +61,12 @@ struct tfhe_ctx {
   uint32_t* d_testvec = nullptr;
   double2* d_tw = nullptr;
   int ksk_stride = 0;
+  // tensor-core key switch (key_switch_mma.cuh): byte planes of the key, K-major, and its TMA descriptor
+  uint8_t* d_ksk_bytes = nullptr;  // [4*ksk_stride][ks_K]
+  long long ks_K = 0;              // N * t * (base - 1); 0 = path unavailable for this parameter set
+  CUtensorMap ks_mapB{};
+  int ks_variant = 0;              // 0 = auto, 1 = row gather (key_switch_kernel), 2 = tensor-core contraction
+  DevBuf ks_sel;                   // selection matrix of the current chunk
   Tw4 tw0{};
   cudaStream_t stream = nullptr;  // used by the host-buffer API
   DevBuf prep, lwe1, tmp, prep2, idx_a, idx_b, ops_dev;       // engine scratch
@@ -246,9 +253,82 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// 2-D u8 tensor [rows][K], K contiguous; box = 128 K-bytes x box_rows, 128-byte swizzle, out-of-range rows read as zero
+int make_ks_map(tfhe_ctx* c, CUtensorMap* m, const void* base, long long K, long long rows, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(c, TFHE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K};
+  const cuuint32_t box[2] = {(cuuint32_t)KSM_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, TFHE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+// Tensor-core path: chunks of <= 8192 ciphertexts (selection matrix <= K * 8192 bytes).
+int launch_key_switch_mma(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s,
+                          const GateDesc* out_gates, long long instances) {
+  const tfhe_params& P = c->P;
+  const long long K = c->ks_K;
+  const int64_t CH = 8192;
+  CK(c, c->ks_sel.reserve((size_t)std::min<int64_t>(count, CH) * K));
+  const int cols = 4 * c->ksk_stride;
+  for (int64_t g0 = 0; g0 < count; g0 += CH) {
+    const int cnt = (int)std::min<int64_t>(CH, count - g0);
+    const uint32_t* src = d_lwe1 + (size_t)g0 * (P.N + 1);
+    ks_onehot_kernel<<<(unsigned)cnt, 256, (size_t)K, s>>>(src, c->ks_sel.as<uint8_t>(), d_out, P.N, P.n, P.basebit, P.iks_t,
+                                                             (int)K, out_gates, instances, (long long)g0);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    CUtensorMap mapA;
+    int rc = make_ks_map(c, &mapA, c->ks_sel.p, K, cnt, KSM_BM);
+    if (rc) return rc;
+    KsMmaArgs a{};
+    a.out = d_out; a.out_gates = out_gates; a.instances = instances; a.g_base = (long long)g0; a.count = cnt; a.n = P.n;
+    a.kblocks = (int)(K / KSM_BK);
+    a.tiles_m = (cnt + KSM_BM - 1) / KSM_BM;
+    a.tiles_n = (cols + KSM_BN - 1) / KSM_BN;
+    // split K so that the work items fill whole waves of SMs; ~8 k-blocks of fixed cost per item (setup + epilogue)
+    const int tiles = a.tiles_m * a.tiles_n;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int ks = 1; ks <= 16 && ks <= a.kblocks; ks++) {
+      const double waves = std::ceil((double)tiles * ks / c->sm_count);
+      const double cost = waves * ((double)a.kblocks / ks + 8.0);
+      if (cost < best_cost) { best_cost = cost; best = ks; }
+    }
+    a.ksplit = best;
+    ks_mma_kernel<<<(unsigned)(tiles * a.ksplit), KSM_THREADS, KSM_SMEM, s>>>(mapA, c->ks_mapB, a);
+    c->launches++;
+    CK(c, cudaGetLastError());
+  }
+  return 0;
+}
+
 int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s,
                       const GateDesc* out_gates = nullptr, long long instances = 1) {
   if (count == 0) return 0;
+  if (c->ks_variant == 2 && !c->ks_K) return fail(c, TFHE_ERR_STATE, "tensor-core key switch is not available for this parameter set");
+  // the dense contraction does (base-1)x the additions of the gather: it wins once the batch fills the SMs with 128-row tiles
+  if (c->ks_K && (c->ks_variant == 2 || (c->ks_variant == 0 && count >= 1024)))
+    return launch_key_switch_mma(c, count, d_lwe1, d_out, s, out_gates, instances);
   const size_t sm = (size_t)c->P.N * c->P.iks_t * sizeof(uint32_t);
   if (sm > 128 * 1024) return fail(c, TFHE_ERR_ARG, "N * iks_t too large for the key-switch kernel");
   key_switch_kernel<<<(unsigned)count, 256, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
@@ -380,6 +460,10 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
     c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
+  if ((e = cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KSM_SMEM)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(ks_mma)", e);
+  if ((e = cudaFuncSetAttribute(ks_onehot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(ks_onehot)", e);
   if ((e = cudaFuncSetAttribute(key_switch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 128 * 1024)) != cudaSuccess)  // a limit shared by every context of the process
     return bail("cudaFuncSetAttribute(key_switch)", e);
@@ -401,6 +485,8 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
   if (c->d_bsk16) cudaFree(c->d_bsk16);
   if (c->d_tw16) cudaFree(c->d_tw16);
   if (c->d_ksk) cudaFree(c->d_ksk);
+  if (c->d_ksk_bytes) cudaFree(c->d_ksk_bytes);
+  c->ks_sel.release();
   if (c->d_testvec) cudaFree(c->d_testvec);
   if (c->d_tw) cudaFree(c->d_tw);
   delete c;
@@ -415,7 +501,7 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
   const tfhe_params& P = c->P;
   const size_t polys = (size_t)P.n * 2 * P.L * 2;
   const int M = P.N / 2;
-  if (!c->d_bsk) CK(c, cudaMalloc(&c->d_bsk, polys * M * sizeof(double2)));
+  if (!c->d_bsk) CK(c, cudaMalloc(&c->d_bsk, polys * M * sizeof(double2) + (size_t)8 * 2 * M * sizeof(double2)));  // + slack for key-row prefetches past the last step
   if (!c->d_testvec) CK(c, cudaMalloc(&c->d_testvec, (size_t)2 * P.N * 4));
   bsk_repack_kernel<<<(unsigned)polys, 128, 0, s>>>(d_bsk_fft, c->d_bsk, P.N);
   c->launches++;
@@ -435,6 +521,20 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
     c->launches++;
     CK(c, cudaGetLastError());
     c->has_ksk = true;
+    // byte planes for the tensor-core key switch: only where the dense product is cheap (base - 1 = 3 rows per digit)
+    c->ks_K = 0;
+    const long long K = (long long)P.N * P.iks_t * ((1 << P.basebit) - 1);
+    if (P.basebit == 2 && K % KSM_BK == 0 && K <= 160 * 1024 && encode_tiled_fn()) {
+      const int cols = 4 * c->ksk_stride;
+      if (!c->d_ksk_bytes) CK(c, cudaMalloc(&c->d_ksk_bytes, (size_t)cols * K));
+      dim3 grid((unsigned)((K + 63) / 64), (unsigned)((c->ksk_stride + 63) / 64));
+      ksk_bytes_repack_kernel<<<grid, 256, 0, s>>>(c->d_ksk, c->d_ksk_bytes, c->ksk_stride, P.basebit, K);
+      c->launches++;
+      CK(c, cudaGetLastError());
+      int rcm = make_ks_map(c, &c->ks_mapB, c->d_ksk_bytes, K, cols, KSM_BN);
+      if (rcm) return rcm;
+      c->ks_K = K;
+    }
   }
   CK(c, cudaStreamSynchronize(s));
   if (!c->bsk_tex) {
@@ -844,6 +944,12 @@ int tfhe_mul_poly_batch(tfhe_ctx* c, int64_t count, const uint32_t* p0, const ui
 }
 
 int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) { return c ? c->launches : 0; }
+
+int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
+  if (!c || variant < 0 || variant > 2) return fail(c, TFHE_ERR_ARG, "key-switch variant must be 0 (auto), 1 (gather) or 2 (tensor core)");
+  c->ks_variant = variant;
+  return TFHE_OK;
+}
 
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;

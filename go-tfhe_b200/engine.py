@@ -186,6 +186,11 @@ class Context:
         v = {"ldg": 0, "tma": 1, "tex": 2, "w16": 3, "tmem": 4, "tmex": 5, "tmex+tma": 6}[variant] if isinstance(variant, str) else int(variant)
         self._ck(self.lib.tfhe_ctx_set_blind_rotate_variant(self.h, v), "tfhe_ctx_set_blind_rotate_variant")
 
+    def set_key_switch_variant(self, variant):
+        """'auto' (default) | 'gather' | 'mma' — row gather out of L2 or one tensor-core contraction; results are identical."""
+        v = {"auto": 0, "gather": 1, "mma": 2}[variant] if isinstance(variant, str) else int(variant)
+        self._ck(self.lib.tfhe_ctx_set_key_switch_variant(self.h, v), "tfhe_ctx_set_key_switch_variant")
+
     def set_timing(self, enable=True):
         self._ck(self.lib.tfhe_ctx_set_timing(self.h, 1 if enable else 0), "tfhe_ctx_set_timing")
 

@@ -169,6 +169,11 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
  * through tensor memory + a lane shuffle (N = 1024), 6 = 5 plus TMA-staged key rows.  All compute identical results;
  * the default is the fastest measured (profiles/r01_experiments.md). */
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
+/* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default), 1 = one block per
+ * ciphertext gathering its N*t*(1-1/base) key rows out of L2, 2 = the whole batch as one exact u8 x u8 -> s32
+ * contraction on the tensor cores (tcgen05.mma kind::i8 over the byte planes of the key; basebit = 2 parameter sets
+ * only).  Both are bit-identical: additions mod 2^32 commute. */
+int tfhe_ctx_set_key_switch_variant(tfhe_ctx* ctx, int variant);
 /* Per-stage device timing for bench.py's roofline: when enabled, every bootstrap batch records CUDA events on
  * its launching stream around the blind-rotate kernel and the key-switch kernel.  tfhe_ctx_collect_timing waits
  * for the recorded events and returns {blind_rotate_ms_total, blind_rotate_launches, key_switch_ms_total,

@@ -113,6 +113,28 @@ def test_sample_extract_and_key_switch_bit_exact(O, gpu):  # rows a16, a17
     assert np.array_equal(ks, np.stack([O.key_switch(P, e, ck.ksk) for e in ext]))
 
 
+@pytest.mark.parametrize("name,count", [("80", 5), ("80", 300), ("128", 131), ("128", 1500)])
+def test_key_switch_tensor_core_bit_exact(O, gpu, name, count):  # row a17 as one u8 x u8 -> s32 contraction (tcgen05)
+    """Both key-switch evaluations (row gather, tensor-core contraction over the key's byte planes) must give the very
+    same words as trgsw/keyswitch.go:10-37 on random inputs: partial 128-row tiles, partial 256-column tiles (n = 550)
+    and split-K accumulation are all exercised."""
+    P, sk, ck, ctx = gpu(name)
+    rng = np.random.default_rng(1000 + count)
+    ext = rng.integers(0, 1 << 32, (count, P.N + 1), dtype=np.uint64).astype(np.uint32)
+    ext[0, : P.N] = 0                      # every digit of the rounded mask words equal: only k = 0 rows (none selected)
+    ext[min(1, count - 1), : P.N] = 0xFFFFFFFF
+    try:
+        ctx.set_key_switch_variant("gather")
+        ref = ctx.key_switch_batch(ext)
+        ctx.set_key_switch_variant("mma")
+        got = ctx.key_switch_batch(ext)
+    finally:
+        ctx.set_key_switch_variant("auto")
+    assert np.array_equal(got, ref)
+    for i in list(range(min(count, 3))) + [count - 1]:
+        assert np.array_equal(got[i], O.key_switch(P, ext[i], ck.ksk))
+
+
 @pytest.mark.parametrize("name", ["80", "110", "128"])
 def test_bootstrap_bit_exact_and_decrypts(O, gpu, name):  # row a18
     P, sk, ck, ctx = gpu(name)
