@@ -26,7 +26,7 @@
 #define TFHE_BR_UNROLL_POLY 2   // 2 = fully unrolled over the A/B polynomials, 1 = rolled
 #endif
 #ifndef TFHE_BR_UNROLL_LVL
-#define TFHE_BR_UNROLL_LVL 8    // >= L = fully unrolled over decomposition levels, 1 = rolled
+#define TFHE_BR_UNROLL_LVL 1    // 1 = level loop rolled (measured best: smaller code, no spills), >= L = fully unrolled
 #endif
 #ifndef TFHE_BR_KEEP_OWN
 #define TFHE_BR_KEEP_OWN 0      // 1: exchanges keep the one point that does not change owner in its register (measured 3.5% slower: the predicated asm blocks pin the schedule)
@@ -44,10 +44,10 @@
 #define TFHE_BR_PAIR_FWD 0      // forward transforms of consecutive decomposition levels run interleaved in pairs
 #endif
 #ifndef TFHE_BR_KPIPE
-#define TFHE_BR_KPIPE 1         // 1: key rows are software-pipelined in registers: the 16 loads of digit r+1 are issued right after the MAC of digit r (across the loop back-edge and into the next step)
+#define TFHE_BR_KPIPE 0         // 1: key rows are software-pipelined in registers: the 16 loads of digit r+1 are issued right after the MAC of digit r (across the loop back-edge and into the next step)
 #endif
 #ifndef TFHE_BR_PF_L1
-#define TFHE_BR_PF_L1 0         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread)
+#define TFHE_BR_PF_L1 1         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread)
 #endif
 // exchange buffers hold one transform ([2][M]) unless a paired mode needs two ([2][2M])
 #define TFHE_BR_EXW ((TFHE_BR_PAIR_INV || TFHE_BR_PAIR_FWD) ? 2 : 1)

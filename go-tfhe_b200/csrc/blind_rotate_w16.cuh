@@ -410,8 +410,15 @@ __global__ void __launch_bounds__(128, MINB) blind_rotate_w16_kernel(const BrW16
 // read-modify-written in 16-column chunks by the multiply-accumulate.  That takes the kernel from 255 to <= 168
 // registers, i.e. from 4 to 6 resident blocks per SM, to overlap the shared-memory and FP64 pipes better.
 // =============================================================================================
+// TFHE_BR_TM_MAXNREG: experiment knob — cap the register count directly (e.g. 200 -> 5 blocks per SM) instead of
+// letting ptxas derive it from the minimum-blocks bound (which only ever picks 255, 168 or 128).
+#ifdef TFHE_BR_TM_MAXNREG
+#define TFHE_BR_TM_BOUNDS(T, MINB) __maxnreg__(TFHE_BR_TM_MAXNREG)
+#else
+#define TFHE_BR_TM_BOUNDS(T, MINB) TFHE_BR_BOUNDS(T, MINB)
+#endif
 template <int LOGN, int L, int BGBIT, bool SMALL, int MINB>
-__global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kernel(const BrArgs A) {
+__global__ void TFHE_BR_TM_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kernel(const BrArgs A) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
   static_assert(T >= 32 && T <= 128, "one TMEM lane per thread");
   constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
