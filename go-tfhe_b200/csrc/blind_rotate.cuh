@@ -49,8 +49,18 @@
 #ifndef TFHE_BR_PF_L1
 #define TFHE_BR_PF_L1 1         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread)
 #endif
+#ifndef TFHE_BR_PF_LATE
+#define TFHE_BR_PF_LATE 0       // 1: the prefetch of the next step's first rows is issued between the two inverse transforms
+#endif
 // exchange buffers hold one transform ([2][M]) unless a paired mode needs two ([2][2M])
-#define TFHE_BR_EXW ((TFHE_BR_PAIR_INV || TFHE_BR_PAIR_FWD) ? 2 : 1)
+#ifndef TFHE_TM_PAIR
+#define TFHE_TM_PAIR 0          // TMEM-accumulator kernel: forward transforms of two levels and the two inverse transforms run paired
+#endif
+#define TFHE_BR_EXW ((TFHE_BR_PAIR_INV || TFHE_BR_PAIR_FWD || TFHE_TM_PAIR) ? 2 : 1)
+#ifndef TFHE_BR_WARP_EX
+#define TFHE_BR_WARP_EX 0       // 1: exchanges whose 8-thread groups lie inside one warp use a third buffer and __syncwarp instead of a block barrier
+#endif
+#define TFHE_BR_NBUF (TFHE_BR_WARP_EX ? 3 : 2)
 #define TFHE_PRAGMA_(x) _Pragma(#x)
 #define TFHE_UNROLL(n) TFHE_PRAGMA_(unroll n)
 
@@ -258,9 +268,15 @@ struct Fft {
   template <int KW, int KR, class Hook>
   __device__ __forceinline__ void exchange(double2 (&x)[8], const Hook& hook) {
     double2* buf = ex;
+    // threads that trade points in this exchange: stride(coarser pass) consecutive threads; inside one warp for the
+    // exchanges next to the last pass (8 threads at N = 1024, 16 at N = 2048)
+    constexpr bool WARP_LOCAL = TFHE_BR_WARP_EX && !SINGLE && (G::stride(KW < KR ? KW : KR) <= 32) && (G::T % 32 == 0);
     if constexpr (SINGLE) {
       mbar_wait(rd_bar, rd_phase);  // every thread has finished reading the previous exchange
       rd_phase ^= 1u;
+    } else if constexpr (WARP_LOCAL) {
+      buf += 2 * TFHE_BR_EXW * G::M;  // third buffer: never touched by a block-wide exchange
+      __syncwarp();                   // the warp has finished reading its groups from the previous warp-local exchange
     } else {
       buf += (parity ? TFHE_BR_EXW * G::M : 0);
       parity ^= 1;
@@ -275,7 +291,8 @@ struct Fft {
       if constexpr (KEEP) sts_if(buf + swz(wb + G::stride(KW) * a), x[a], a != own);
       else buf[swz(wb + G::stride(KW) * a)] = x[a];
     }
-    __syncthreads();
+    if constexpr (WARP_LOCAL) __syncwarp();
+    else __syncthreads();
     hook();
 #pragma unroll
     for (int a = 0; a < 8; a++) {
@@ -497,9 +514,13 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
     const int rowB = rowA + M;
 #if TFHE_BR_PF_L1
     if constexpr (!std::is_same<Key, KeyTex>::value) {  // rows of digit r + d (contiguous into the next step's row-set)
-      const char* pf = reinterpret_cast<const char*>(bk.p + (r + TFHE_BR_PF_L1) * 2 * M) + tau * 128;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
+      // rows that belong to the NEXT step are requested later (between the two inverse transforms): issued here they
+      // would have to survive both inverse transforms in an L1 that four blocks stream 96 KiB per step through
+      if (!TFHE_BR_PF_LATE || r + TFHE_BR_PF_L1 < 2 * L) {
+        const char* pf = reinterpret_cast<const char*>(bk.p + (r + TFHE_BR_PF_L1) * 2 * M) + tau * 128;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
+      }
     }
 #endif
 #pragma unroll
@@ -575,6 +596,16 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
     acc[j] += to_torus<SMALL>(accA[a].x);
     acc[j + M] += to_torus<SMALL>(accA[a].y);
   }
+#if TFHE_BR_PF_L1 && TFHE_BR_PF_LATE
+  if constexpr (!std::is_same<Key, KeyTex>::value) {
+#pragma unroll
+    for (int d = 0; d < TFHE_BR_PF_L1; d++) {
+      const char* pf = reinterpret_cast<const char*>(bk.p + (2 * L + d) * 2 * M) + tau * 128;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
+    }
+  }
+#endif
 #if !TFHE_BR_PAIR_INV
   fft.inverse(accB, tw0);
 #endif
@@ -588,7 +619,7 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
 
 template <int LOGN>
 constexpr size_t br_smem_bytes(int n) {
-  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [2][EXW][M]*/ +
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)TFHE_BR_NBUF * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [NBUF][EXW][M]*/ +
          (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
 }
 
@@ -608,7 +639,7 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][EXW][M]
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 32 * TFHE_BR_EXW * M);
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * TFHE_BR_NBUF * TFHE_BR_EXW * M);
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   const int n = A.n;
@@ -900,7 +931,7 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const Cmu
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);       // holds ct0, becomes the result
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);
-  uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 32 * TFHE_BR_EXW * M);  // [2][N]
+  uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 16 * TFHE_BR_NBUF * TFHE_BR_EXW * M);  // [2][N]
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   for (int j = tau; j < 2 * N; j += T) {

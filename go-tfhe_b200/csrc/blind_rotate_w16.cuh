@@ -427,7 +427,7 @@ __global__ void TFHE_BR_TM_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
   __shared__ uint32_t s_tmem_base;
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][EXW][M]
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 32 * TFHE_BR_EXW * M);
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * TFHE_BR_NBUF * TFHE_BR_EXW * M);
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   const int n = A.n;
@@ -472,8 +472,66 @@ __global__ void TFHE_BR_TM_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
         dre[a] = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
         dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
       }
+      int lvl0 = 0;
+#if TFHE_TM_PAIR
+      // two levels at a time: one block barrier and one burst of shared-memory traffic per exchange for both transforms
+      auto mac_tm = [&](const double2 (&x)[8], int r) {
+        const double2* __restrict__ rowA = bk + (size_t)(r * 2 + 0) * M;
+        const double2* __restrict__ rowB = rowA + M;
+        double2 ka[8], kb[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) { ka[e] = __ldg(rowA + e * T); kb[e] = __ldg(rowB + e * T); }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          double2 aA[4], aB[4];
+          uint32_t ra[16], rb[16];
+          if (r > 0) {
+            tmem_ld16(tacc + 16 * h, ra);
+            tmem_ld16(tacc + 32 + 16 * h, rb);
+            tmem_wait_ld();
+            unpack4(ra, aA);
+            unpack4(rb, aB);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) { aA[q] = make_double2(0.0, 0.0); aB[q] = make_double2(0.0, 0.0); }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int e = 4 * h + q;
+            aA[q].x = fma(x[e].x, ka[e].x, aA[q].x);
+            aA[q].x = fma(-x[e].y, ka[e].y, aA[q].x);
+            aA[q].y = fma(x[e].x, ka[e].y, aA[q].y);
+            aA[q].y = fma(x[e].y, ka[e].x, aA[q].y);
+            aB[q].x = fma(x[e].x, kb[e].x, aB[q].x);
+            aB[q].x = fma(-x[e].y, kb[e].y, aB[q].x);
+            aB[q].y = fma(x[e].x, kb[e].y, aB[q].y);
+            aB[q].y = fma(x[e].y, kb[e].x, aB[q].y);
+          }
+          pack4(aA, ra);
+          pack4(aB, rb);
+          tmem_st16(tacc + 16 * h, ra);
+          tmem_st16(tacc + 32 + 16 * h, rb);
+        }
+        tmem_wait_st();
+      };
 #pragma unroll 1
-      for (int lvl = 0; lvl < L; lvl++) {
+      for (; lvl0 + 1 < L; lvl0 += 2) {
+        double2 x[8], y[8];
+        const int sh0 = 32 - (lvl0 + 1) * BGBIT, sh1 = 32 - (lvl0 + 2) * BGBIT;
+#pragma unroll
+        for (int a = 0; a < 8; a++) {
+          x[a].x = field_to_double((dre[a] >> sh0) & MASK, BIAS);
+          x[a].y = field_to_double((dim[a] >> sh0) & MASK, BIAS);
+          y[a].x = field_to_double((dre[a] >> sh1) & MASK, BIAS);
+          y[a].y = field_to_double((dim[a] >> sh1) & MASK, BIAS);
+        }
+        fft.forward2(x, y, A.tw0);
+        mac_tm(x, poly * L + lvl0);
+        mac_tm(y, poly * L + lvl0 + 1);
+      }
+#endif
+#pragma unroll 1
+      for (int lvl = lvl0; lvl < L; lvl++) {
         const int r = poly * L + lvl;
         const int sh = 32 - (lvl + 1) * BGBIT;
         double2 x[8];
@@ -603,6 +661,32 @@ __global__ void TFHE_BR_TM_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
         tmem_wait_st();
       }
     }
+#if TFHE_TM_PAIR
+    {
+      double2 x[8], y[8];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint32_t ra[16], rb[16];
+        double2 v[4], w[4];
+        tmem_ld16(tacc + 16 * h, ra);
+        tmem_ld16(tacc + 32 + 16 * h, rb);
+        tmem_wait_ld();
+        unpack4(ra, v);
+        unpack4(rb, w);
+#pragma unroll
+        for (int q = 0; q < 4; q++) { x[4 * h + q] = v[q]; y[4 * h + q] = w[q]; }
+      }
+      fft.inverse2(x, y, A.tw0);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        acc[j] += to_torus<SMALL>(x[a].x);
+        acc[j + M] += to_torus<SMALL>(x[a].y);
+        acc[N + j] += to_torus<SMALL>(y[a].x);
+        acc[N + j + M] += to_torus<SMALL>(y[a].y);
+      }
+    }
+#else
 #pragma unroll 1
     for (int poly = 0; poly < 2; poly++) {
       double2 x[8];
@@ -625,6 +709,7 @@ __global__ void TFHE_BR_TM_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
         P[j + M] += to_torus<SMALL>(x[a].y);
       }
     }
+#endif
     __syncthreads();
   }
 

@@ -451,6 +451,10 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   }
   if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)  // limit, not allocation: n <= 4096
     return bail("cudaFuncSetAttribute(blind_rotate)", e);
+  if (const char* co = getenv("TFHE_B200_EXP_CARVEOUT")) {  // experiment only: shared-memory carve-out in percent (L1 gets the rest)
+    if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co))) != cudaSuccess)
+      return bail("cudaFuncSetAttribute(carveout)", e);
+  }
   if ((e = cudaFuncSetAttribute(V.br_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_staged_smem(4096))) !=
       cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_staged)", e);
@@ -917,7 +921,7 @@ static int poly_call(tfhe_ctx* c, int mode, int64_t count, const void* in0, size
   PolyArgs a{};
   a.in0 = c->h2d_a.p; a.in1 = c->h2d_b.p; a.out = c->d2h_out.p; a.tw_tab = c->d_tw; a.mode = mode; a.tw0 = c->tw0;
   const int N = c->P.N, T = N / 16;
-  const size_t sm = (size_t)2 * TFHE_BR_EXW * (N / 2) * 16;
+  const size_t sm = (size_t)TFHE_BR_NBUF * TFHE_BR_EXW * (N / 2) * 16;
   switch (c->logN) {
     case 9: poly_kernel<9><<<(unsigned)count, T, sm, c->stream>>>(a); break;
     case 10: poly_kernel<10><<<(unsigned)count, T, sm, c->stream>>>(a); break;
