@@ -139,15 +139,22 @@ __global__ void __launch_bounds__(256) key_switch_kernel(const uint32_t* __restr
   const uint32_t prec = 1u << (32 - (1 + basebit * t));
   const uint32_t mask = (1u << basebit) - 1u;
   const int base = 1 << basebit;
+  // Large bases (Uint sets: base = 64, key 1.57 GiB > L2): keep the rows in (i, j) order and include the k = 0 rows
+  // (all-zero in the key, cloudkey.go:111; 1/base of the traffic).  Every block then walks the key in the same order,
+  // so co-resident ciphertexts (each row is wanted by count/base of them) meet in L2 instead of each streaming its
+  // rows from HBM.  Small bases: compact away the k = 0 rows (1/4 of them at base 4); order is irrelevant there
+  // because the whole key is L2-resident.
+  const bool ordered = basebit >= 4;
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const uint32_t abar = src[i] + prec;
     for (int j = 0; j < t; j++) {
       const uint32_t k = (abar >> (32 - (j + 1) * basebit)) & mask;
-      if (k != 0) rows[atomicAdd(&nrows, 1)] = (uint32_t)(base * t * i + base * j) + k;
+      if (ordered) rows[i * t + j] = (uint32_t)(base * t * i + base * j) + k;
+      else if (k != 0) rows[atomicAdd(&nrows, 1)] = (uint32_t)(base * t * i + base * j) + k;
     }
   }
   __syncthreads();
-  const int cnt = nrows;
+  const int cnt = ordered ? N * t : nrows;
   const int ncol4 = stride / 4;
   for (int c4 = threadIdx.x; c4 < ncol4; c4 += blockDim.x) {
     uint4 acc = make_uint4(0u, 0u, 0u, 0u);

@@ -295,6 +295,13 @@ def test_circuit_full_adder_and_ripple_carry_bit_exact(T, O, gpu):
         wires[o] = O.gate_batch(ck, op, wires[a], wires[b])
     for k, w in enumerate(circ.out_wires):
         assert np.array_equal(got[k], wires[w])
+    # same circuit with every level's key switch on the tensor-core path (job -> wire scatter inside its epilogue)
+    try:
+        ctx.set_key_switch_variant("mma")
+        got2 = ctx.circuit_run(circ.gates, 2 * bits + 1, np.concatenate([ins, cst]), circ.out_wires)
+    finally:
+        ctx.set_key_switch_variant("auto")
+    assert np.array_equal(got2, got)
 
 
 def test_circuit_mux_not_copy_and_errors(T, O, gpu):

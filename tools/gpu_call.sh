@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-( VARIANTS="ldg" bash tools/exp_variants.sh ) > gpurun_out/c10_variants.txt 2>&1
-grep "^==\|^BR" gpurun_out/c10_variants.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/c12_pytest.txt 2>&1; tail -3 gpurun_out/c12_pytest.txt
+timeout 900 python tools/bench_configs.py c4 > gpurun_out/c12_configs.txt 2>&1; cat gpurun_out/c12_configs.txt
