@@ -46,3 +46,20 @@ def NewCloudKey(secretKey, seed=1, threads=None, with_ksk=True):
                                            ctypes.byref(off), tv.ctypes.data, ksk.ctypes.data if with_ksk else None,
                                            bsk.ctypes.data)
     return CloudKey(P, off.value, tv, ksk, bsk)
+
+
+def NewCloudKeyOnDevice(secretKey, seed=1, device=0, with_ksk=True, export=True):
+    """cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-31) evaluated on the GPU (tfhe_ctx_generate_cloudkey): the
+    bootstrapping and key-switching keys are produced in device memory and left loaded in the engine; with export=True
+    the returned CloudKey also carries the reference-layout fields (what a Go caller would store), otherwise only the
+    engine handle."""
+    P = secretKey.P
+    ctx = engine.Context(P, device)
+    res = ctx.generate_cloudkey(secretKey.KeyLv0, secretKey.KeyLv1, seed, with_ksk, export)
+    if export:
+        off, tv, ksk, bsk = res
+        ck = CloudKey(P, off, tv, ksk, bsk)
+    else:
+        ck = CloudKey(P, 0, None, None, None)
+    ck._ctx[device] = ctx
+    return ck

@@ -21,6 +21,7 @@
 #include "blind_rotate_tx.cuh"
 #include "lwe_kernels.cuh"
 #include "key_switch_mma.cuh"
+#include "keygen.cuh"
 
 using namespace tfhe;
 
@@ -577,6 +578,70 @@ int tfhe_ctx_load_cloudkey(tfhe_ctx* c, uint32_t offset, const double* bsk_fft, 
                                        c->stream);
   sb.release(); sk.release(); st.release();
   if (e != cudaSuccess) return fail(c, TFHE_ERR_CUDA, "key upload: %s", cudaGetErrorString(e));
+  return rc;
+}
+
+// cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-145) on the device; see keygen.cuh.
+int tfhe_ctx_generate_cloudkey(tfhe_ctx* c, const uint32_t* key_lv0, const uint32_t* key_lv1, double alpha_lv0,
+                               double alpha_lv1, uint64_t seed, int with_ksk, uint32_t* offset_out, double* bsk_fft_out,
+                               uint32_t* ksk_out, uint32_t* testvec_out) {
+  if (!c || !key_lv0 || !key_lv1) return fail(c, TFHE_ERR_ARG, "null argument");
+  if (!(alpha_lv0 >= 0.0) || !(alpha_lv1 >= 0.0)) return fail(c, TFHE_ERR_ARG, "noise parameters must be >= 0");
+  if (ksk_out && !with_ksk) return fail(c, TFHE_ERR_ARG, "ksk_out given but with_ksk = 0");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const tfhe_params& P = c->P;
+  const size_t bsk_bytes = (size_t)P.n * 2 * P.L * 2 * P.N * sizeof(double);
+  const size_t ksk_rows = (size_t)P.N * P.iks_t * (1u << P.basebit);
+  const size_t ksk_bytes = ksk_rows * (P.n + 1) * 4;
+  const size_t tv_bytes = (size_t)2 * P.N * 4;
+  // genDecompositionOffset (cloudkey.go:60-71) and genTestvec (:74-85: A = 0, B = F64ToTorus(0.125))
+  uint32_t offset = 0;
+  for (int i = 0; i < P.L; i++) offset += (uint32_t)(1u << (P.bgbit - 1)) * (uint32_t)(1u << (32 - (i + 1) * P.bgbit));
+  std::vector<uint32_t> tv((size_t)2 * P.N, 0u);
+  for (int i = 0; i < P.N; i++) tv[P.N + i] = 0x20000000u;
+  DevBuf s0, s1, sb, sk, st;
+  cudaStream_t s = c->stream;
+  cudaError_t e = s0.reserve((size_t)P.n * 4);
+  if (e == cudaSuccess) e = s1.reserve((size_t)P.N * 4);
+  if (e == cudaSuccess) e = sb.reserve(bsk_bytes);
+  if (e == cudaSuccess && with_ksk) e = sk.reserve(ksk_bytes);
+  if (e == cudaSuccess) e = st.reserve(tv_bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s0.p, key_lv0, (size_t)P.n * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s1.p, key_lv1, (size_t)P.N * 4, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(st.p, tv.data(), tv_bytes, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    KeygenBskArgs a{};
+    a.bsk_fft = sb.as<double>(); a.s0 = s0.as<uint32_t>(); a.s1 = s1.as<uint32_t>(); a.tw_tab = c->d_tw; a.alpha = alpha_lv1;
+    a.seed = seed; a.L = P.L; a.bgbit = P.bgbit; a.tw0 = c->tw0;
+    const unsigned grid = (unsigned)((size_t)P.n * 2 * P.L);
+    const int T = P.N / 16;
+    const size_t sm = (size_t)TFHE_BR_NBUF * TFHE_BR_EXW * (P.N / 2) * 16;
+    switch (c->logN) {
+      case 9: keygen_bsk_kernel<9><<<grid, T, sm, s>>>(a); break;
+      case 10: keygen_bsk_kernel<10><<<grid, T, sm, s>>>(a); break;
+      default: keygen_bsk_kernel<11><<<grid, T, sm, s>>>(a); break;
+    }
+    c->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess && with_ksk) {
+    keygen_ksk_kernel<<<(unsigned)ksk_rows, 128, 0, s>>>(sk.as<uint32_t>(), s0.as<uint32_t>(), s1.as<uint32_t>(), P.n, P.basebit,
+                                                        P.iks_t, alpha_lv0, seed);
+    c->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess)
+    rc = tfhe_ctx_load_cloudkey_device(c, offset, sb.as<double>(), with_ksk ? sk.as<uint32_t>() : nullptr, st.as<uint32_t>(), s);
+  if (e == cudaSuccess && rc == 0) {  // hand the CloudKey fields back in the reference's layouts
+    if (offset_out) *offset_out = offset;
+    if (bsk_fft_out) e = cudaMemcpy(bsk_fft_out, sb.p, bsk_bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && ksk_out) e = cudaMemcpy(ksk_out, sk.p, ksk_bytes, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && testvec_out) memcpy(testvec_out, tv.data(), tv_bytes);
+  }
+  cudaStreamSynchronize(s);
+  s0.release(); s1.release(); sb.release(); sk.release(); st.release();
+  if (e != cudaSuccess) return fail(c, TFHE_ERR_CUDA, "key generation: %s", cudaGetErrorString(e));
   return rc;
 }
 

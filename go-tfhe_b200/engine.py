@@ -74,6 +74,21 @@ class Context:
         self._ck(self.lib.tfhe_ctx_load_cloudkey(self.h, ctypes.c_uint32(offset), _ptr(bsk), _ptr(k), _ptr(tv)),
                  "tfhe_ctx_load_cloudkey")
 
+    def generate_cloudkey(self, key_lv0, key_lv1, seed=1, with_ksk=True, export=True):
+        """cloudkey.NewCloudKey on the device (tfhe_ctx_generate_cloudkey).  Returns (offset, testvec, ksk, bsk_fft) in the
+        reference layouts when export=True (ksk None without a key-switching key), else None; the key stays loaded."""
+        P = self.P
+        s0, s1 = _u32(key_lv0), _u32(key_lv1)
+        assert s0.size == P.n and s1.size == P.N
+        off = ctypes.c_uint32(0)
+        tv = np.zeros((2, P.N), dtype=np.uint32) if export else None
+        ksk = np.zeros((P.ksk_rows, P.n + 1), dtype=np.uint32) if (export and with_ksk) else None
+        bsk = np.zeros((P.n, 2 * P.L, 2, P.N), dtype=np.float64) if export else None
+        self._ck(self.lib.tfhe_ctx_generate_cloudkey(self.h, _ptr(s0), _ptr(s1), P.alpha_lv0, P.alpha_lv1, int(seed) & (2**64 - 1),
+                                                     1 if with_ksk else 0, ctypes.cast(ctypes.byref(off), ctypes.c_void_p),
+                                                     _ptr(bsk), _ptr(ksk), _ptr(tv)), "tfhe_ctx_generate_cloudkey")
+        return (off.value, tv, ksk, bsk) if export else None
+
     def load_cloudkey_device(self, offset, d_bsk_fft, d_ksk, d_testvec, stream=0):
         self._ck(self.lib.tfhe_ctx_load_cloudkey_device(self.h, ctypes.c_uint32(offset), d_bsk_fft, d_ksk, d_testvec,
                                                         stream), "tfhe_ctx_load_cloudkey_device")

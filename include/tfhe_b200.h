@@ -82,6 +82,16 @@ const char* tfhe_last_error(const tfhe_ctx* ctx);
  * tfhe_blind_rotate_batch is used (cloudkey.NewCloudKeyNoKSK, cloudkey.go:34-57). */
 int tfhe_ctx_load_cloudkey(tfhe_ctx* ctx, uint32_t decomposition_offset, const double* bsk_fft,
                            const uint32_t* ksk, const uint32_t* testvec);
+/* cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-145) evaluated on the device from the caller's secret key
+ * (key.SecretKey.KeyLv0 [n], KeyLv1 [N], binary, as u32): genBootstrappingKey (:122-145: trgsw.EncryptTorus
+ * trgsw/trgsw.go:32-58 over trlwe.EncryptF64 trlwe/trlwe.go:28-50, then NewTRGSWLv1FFT :72-82), genKeySwitchingKey
+ * (:88-120, tlwe.EncryptF64 tlwe/tlwe.go:36-52 with alpha_lv0 = params.KSKAlpha()), genTestvec, genDecompositionOffset.
+ * alpha_lv1 = params.BSKAlpha().  The reference seeds from unseeded math/rand; here the key is a deterministic
+ * function of (secret key, seed).  The key is left loaded in ctx; the optional outputs receive the CloudKey fields in
+ * the layouts of tfhe_ctx_load_cloudkey (any of them may be NULL; ksk_out requires with_ksk != 0). */
+int tfhe_ctx_generate_cloudkey(tfhe_ctx* ctx, const uint32_t* key_lv0, const uint32_t* key_lv1, double alpha_lv0,
+                               double alpha_lv1, uint64_t seed, int with_ksk, uint32_t* decomposition_offset_out,
+                               double* bsk_fft_out, uint32_t* ksk_out, uint32_t* testvec_out);
 /* Same, from buffers already in this device's memory (e.g. filled by one NCCL broadcast from
  * rank 0).  `stream` is a cudaStream_t (0 = default stream); returns after the repack is done. */
 int tfhe_ctx_load_cloudkey_device(tfhe_ctx* ctx, uint32_t decomposition_offset, const double* d_bsk_fft,
