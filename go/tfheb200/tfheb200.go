@@ -125,6 +125,55 @@ func New(ck *cloudkey.CloudKey, device int) *Engine {
 	return e
 }
 
+// NewCloudKeyOnDevice is cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-31) with the key material generated in GPU
+// memory (tfhe_ctx_generate_cloudkey): the returned CloudKey holds the same fields in the same formats as the Go
+// generator's, and the engine that made it is registered for it, so gates.* use it without a second upload.
+func NewCloudKeyOnDevice(keyLv0, keyLv1 []params.Torus, seed uint64, device int) *cloudkey.CloudKey {
+	g, l0 := params.GetTRGSWLv1(), params.GetTLWELv0()
+	p := C.tfhe_params{n: C.int32_t(l0.N), N: C.int32_t(g.N), L: C.int32_t(g.L), bgbit: C.int32_t(g.BGBIT),
+		basebit: C.int32_t(g.BASEBIT), iks_t: C.int32_t(g.IKS_T)}
+	var ctx *C.tfhe_ctx
+	if rc := C.tfhe_ctx_create(&p, C.int(device), &ctx); rc != 0 {
+		panic("tfhe_ctx_create: " + C.GoString(C.tfhe_last_error(nil)))
+	}
+	e := &Engine{ctx: ctx, n: l0.N, bigN: g.N}
+	runtime.SetFinalizer(e, func(e *Engine) { C.tfhe_ctx_destroy(e.ctx) })
+	rows := g.N * g.IKS_T * (1 << g.BASEBIT)
+	bsk := make([]float64, l0.N*2*g.L*2*g.N)
+	ksk := make([]uint32, rows*(l0.N+1))
+	tv := make([]uint32, 2*g.N)
+	var off C.uint32_t
+	e.check(C.tfhe_ctx_generate_cloudkey(ctx, (*C.uint32_t)(unsafe.Pointer(&keyLv0[0])), (*C.uint32_t)(unsafe.Pointer(&keyLv1[0])),
+		C.double(params.KSKAlpha()), C.double(params.BSKAlpha()), C.uint64_t(seed), 1, &off, (*C.double)(&bsk[0]),
+		(*C.uint32_t)(&ksk[0]), (*C.uint32_t)(&tv[0])), "tfhe_ctx_generate_cloudkey")
+	ck := &cloudkey.CloudKey{DecompositionOffset: params.Torus(off), BlindRotateTestvec: trlwe.NewTRLWELv1()}
+	for i := 0; i < g.N; i++ {
+		ck.BlindRotateTestvec.A[i], ck.BlindRotateTestvec.B[i] = params.Torus(tv[i]), params.Torus(tv[g.N+i])
+	}
+	ck.KeySwitchingKey = make([]*tlwe.TLWELv0, rows)
+	for r := range ck.KeySwitchingKey {
+		t := tlwe.NewTLWELv0()
+		for w := 0; w <= l0.N; w++ {
+			t.P[w] = params.Torus(ksk[r*(l0.N+1)+w])
+		}
+		ck.KeySwitchingKey[r] = t
+	}
+	ck.BootstrappingKey = make([]*trgsw.TRGSWLv1FFT, l0.N)
+	for i := range ck.BootstrappingKey {
+		row := &trgsw.TRGSWLv1FFT{TRLWEFFT: make([]trgsw.TRLWELv1FFT, 2*g.L)}
+		for r := range row.TRLWEFFT {
+			o := ((i*2*g.L + r) * 2) * g.N
+			row.TRLWEFFT[r].A.Coeffs = bsk[o : o+g.N : o+g.N]
+			row.TRLWEFFT[r].B.Coeffs = bsk[o+g.N : o+2*g.N : o+2*g.N]
+		}
+		ck.BootstrappingKey[i] = row
+	}
+	enginesMu.Lock()
+	engines[ck] = e
+	enginesMu.Unlock()
+	return ck
+}
+
 func appendTorus(dst []uint32, src []params.Torus) []uint32 {
 	// params.Torus is uint32 (params/params.go:27): same memory layout
 	return append(dst, unsafe.Slice((*uint32)(unsafe.Pointer(&src[0])), len(src))...)
