@@ -15,12 +15,21 @@ ctx.cmux_batch(0, c0, c1)
 ct = T.tlwe.EncryptBool([0, 1, 1], sk, 3)
 ct[:, 24:P.n] = 0  # a~ = 0 => skipped steps: keeps the sanitizer run short
 ref = None
-for v in ("ldg", "tma", "tex", "w16", "tmem"):
+only = [a.split("=")[1] for a in sys.argv if a.startswith("--variant=")]
+for v in (("ldg",) if "--default-only" in sys.argv else (only or ("ldg", "tma", "tex", "w16", "tmem", "tmex", "tmex+tma"))):
     ctx.set_blind_rotate_variant(v)
     out = ctx.blind_rotate_batch(ct)
     ref = out if ref is None else ref
     assert np.array_equal(out, ref), v
 ctx.set_blind_rotate_variant("ldg")
-ctx.key_switch_batch(ctx.sample_extract_batch(ref))
+ext = ctx.sample_extract_batch(ref)
+ks = ctx.key_switch_batch(ext)
+ctx.set_key_switch_variant("mma")   # tensor-core key switch (TMA + tcgen05 + TMEM), partial tiles
+ext200 = np.tile(ext, (67, 1))[:200]
+assert np.array_equal(ctx.key_switch_batch(ext200)[:3], ks)
+ctx.set_key_switch_variant("auto")
 ctx.gate_batch(["MUX", "NOT", "XOR"], ct, ct, ct)
+ck2 = T.cloudkey.NewCloudKeyOnDevice(sk, 5)   # device key generation kernels
+assert list(T.tlwe.DecryptBool(T.gates.NAND(ct[:1] * 0 + T.tlwe.EncryptBool([1], sk, 9), T.tlwe.EncryptBool([1], sk, 10), ck2), sk)) == [0]
+ck2.close()
 print("sanitize workload done")
