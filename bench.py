@@ -16,6 +16,7 @@ one batch of synthetic NAND gates: BASELINE.json configs[1], 4096 gates at 128-b
 """
 import argparse
 import importlib
+import atexit
 import json
 import os
 import statistics
@@ -56,14 +57,17 @@ class ClockSampler:
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            atexit.register(self.proc.kill)  # never leave the sampler behind if the run aborts
         except OSError:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, since=0.0):
+        """Statistics over the samples that arrived after `since` (perf_counter): the sampler is started before the
+        warm-up, because nvidia-smi can take longer to start than the whole timed region lasts (8 ranks at once)."""
         if self.proc:
             self.proc.terminate()
             try:
@@ -71,7 +75,9 @@ class ClockSampler:
             except Exception:
                 pass
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < since:
+                continue
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -227,6 +233,8 @@ def main():
         torch.cuda.synchronize()
 
     # --- warm-up (also validates the result) -------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
@@ -235,13 +243,11 @@ def main():
         raise SystemExit("rank %d: decrypted NAND outputs are wrong" % rank)
 
     # --- timed region: K steps, inputs resident in HBM, L2 flushed between steps (outside the event pairs) --
-    sampler = ClockSampler(local)
     ctx.set_timing(True)
     ctx.collect_timing()
     launches0 = ctx.kernel_launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    sampler.start()
     t_wall0 = time.perf_counter()
     for s0, s1 in ev:
         flush.fill_(1)
@@ -250,7 +256,6 @@ def main():
         s1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     launches = ctx.kernel_launches - launches0
     stage = ctx.collect_timing()
     ctx.set_timing(False)
@@ -265,6 +270,7 @@ def main():
         step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop(since=t_wall0)  # samples taken during the device-timed and the end-to-end timed regions
     got = out_h.numpy().view(np.uint32)
     if not np.array_equal(T.tlwe.DecryptBool(got, sk), 1 - (A & B)):
         raise SystemExit("rank %d: e2e outputs are wrong" % rank)

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-for v in tma tex w16 tmem tmex tmex+tma; do echo "== $v"; timeout 600 compute-sanitizer --tool synccheck python tools/sanitize.py --variant=$v 2>&1 | grep -v "^=========     " | grep "=========\|done" | head -5; done > gpurun_out/c18_synccheck.txt 2>&1
-cat gpurun_out/c18_synccheck.txt
+timeout 600 python bench.py > gpurun_out/c20_bench.txt 2>&1; tail -1 gpurun_out/c20_bench.txt | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['clocks'], d['roofline']['frac'], d['gpu_launches'])"
