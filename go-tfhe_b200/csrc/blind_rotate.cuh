@@ -52,6 +52,9 @@
 #ifndef TFHE_BR_PF_LATE
 #define TFHE_BR_PF_LATE 0       // 1: the prefetch of the next step's first rows is issued between the two inverse transforms
 #endif
+#ifndef TFHE_BR_KO
+#define TFHE_BR_KO 0            // TIMING EXPERIMENTS ONLY (wrong results): bit 0 = no exchanges, bit 1 = no key loads, bit 2 = no barrier in exchanges
+#endif
 // exchange buffers hold one transform ([2][M]) unless a paired mode needs two ([2][2M])
 #ifndef TFHE_TM_PAIR
 #define TFHE_TM_PAIR 0          // TMEM-accumulator kernel: forward transforms of two levels and the two inverse transforms run paired
@@ -281,6 +284,7 @@ struct Fft {
       buf += (parity ? TFHE_BR_EXW * G::M : 0);
       parity ^= 1;
     }
+    if (TFHE_BR_KO & 1) return;
     const int wb = G::base(KW, tau), rb = G::base(KR, tau);
     // Between two full passes exactly one of a thread's 8 points keeps both its owner and its register slot
     // (slot (tau / finer stride) % 8): it stays in its register, skipping 1/8 of the shared-memory traffic.
@@ -292,7 +296,7 @@ struct Fft {
       else buf[swz(wb + G::stride(KW) * a)] = x[a];
     }
     if constexpr (WARP_LOCAL) __syncwarp();
-    else __syncthreads();
+    else if (!(TFHE_BR_KO & 4)) __syncthreads();
     hook();
 #pragma unroll
     for (int a = 0; a < 8; a++) {
@@ -483,7 +487,10 @@ __device__ __forceinline__ uint32_t rot_read(const uint32_t* P, int idx) {
 // key-row fetch policies for the MAC: straight LDG (LSU pipe) or texture fetch (TEX pipe)
 struct KeyLdg {
   const double2* __restrict__ p;
-  __device__ __forceinline__ double2 operator()(int idx) const { return __ldg(p + idx); }
+  __device__ __forceinline__ double2 operator()(int idx) const {
+    if (TFHE_BR_KO & 2) return make_double2(1e-9 * idx, 2e-9 * idx);
+    return __ldg(p + idx);
+  }
 };
 struct KeyTex {
   cudaTextureObject_t tex;
