@@ -20,6 +20,9 @@
 
 #include "blind_rotate.cuh"
 
+#ifndef TFHE_TM_PF_L1
+#define TFHE_TM_PF_L1 0   // d > 0: prefetch.global.L1 of the key rows d digits ahead (block-per-gate TMEM kernel)
+#endif
 #ifndef TFHE_TM_EARLY_BK
 #define TFHE_TM_EARLY_BK 0
 #endif
@@ -542,6 +545,13 @@ __global__ void TFHE_BR_TM_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
         }
         const double2* __restrict__ rowA = bk + (size_t)(r * 2 + 0) * M;
         const double2* __restrict__ rowB = rowA + M;
+#if TFHE_TM_PF_L1
+        {  // L1 prefetch of the NEXT digit's rows (contiguous into the next step's row-set): no registers held in flight
+          const char* pf = reinterpret_cast<const char*>(A.bsk + row_stride * i + (size_t)(r + TFHE_TM_PF_L1) * 2 * M) + tau * 128;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
+        }
+#endif
 #if TFHE_TM_EARLY_BK
         // all 16 key values requested BEFORE the last register pass: the L2 latency hides behind 72 FMAs
         fft.forward_head(x, A.tw0);

@@ -452,10 +452,6 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   }
   if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)  // limit, not allocation: n <= 4096
     return bail("cudaFuncSetAttribute(blind_rotate)", e);
-  if (const char* co = getenv("TFHE_B200_EXP_CARVEOUT")) {  // experiment only: shared-memory carve-out in percent (L1 gets the rest)
-    if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(co))) != cudaSuccess)
-      return bail("cudaFuncSetAttribute(carveout)", e);
-  }
   if ((e = cudaFuncSetAttribute(V.br_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_staged_smem(4096))) !=
       cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_staged)", e);
