@@ -238,9 +238,17 @@ __device__ __forceinline__ int swz(int p) { return p ^ ((p >> 3) & 7); }
 // SINGLE = false: two exchange buffers used alternately (one block barrier per exchange).
 // SINGLE = true : one exchange buffer; the write-after-read hazard is covered by an mbarrier on which every thread
 //                 arrives (non-blocking) after its reads and waits before its next writes (normally long complete).
-template <int LOGM, bool SINGLE = false>
+// NAMED = true : the transform's threads are one of several independent groups of T threads inside a bigger block
+//                 (several gates per block): exchanges synchronise on the named barrier `bar_id` (1..15) instead of
+//                 the whole block.
+template <int LOGM, bool SINGLE = false, bool NAMED = false>
 struct Fft {
   using G = Geo<LOGM>;
+  int bar_id = 0;
+  __device__ __forceinline__ void group_barrier() const {
+    if constexpr (NAMED) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(G::T) : "memory");
+    else __syncthreads();
+  }
   uint64_t* rd_bar = nullptr;
   uint32_t rd_phase = 0;
   // Per-thread persistent state: twiddles of the last pass (unique per thread) and the ping-pong
@@ -296,7 +304,7 @@ struct Fft {
       else buf[swz(wb + G::stride(KW) * a)] = x[a];
     }
     if constexpr (WARP_LOCAL) __syncwarp();
-    else if (!(TFHE_BR_KO & 4)) __syncthreads();
+    else if (!(TFHE_BR_KO & 4)) group_barrier();
     hook();
 #pragma unroll
     for (int a = 0; a < 8; a++) {

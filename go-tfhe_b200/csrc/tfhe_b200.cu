@@ -19,6 +19,8 @@
 #include "blind_rotate.cuh"
 #include "blind_rotate_w16.cuh"
 #include "blind_rotate_tx.cuh"
+#include "blind_rotate_tms.cuh"
+#include "blind_rotate_mg.cuh"
 #include "lwe_kernels.cuh"
 #include "key_switch_mma.cuh"
 #include "keygen.cuh"
@@ -154,7 +156,29 @@ struct Variant {
   void (*br_tm)(const BrArgs);       // block-per-gate, TMEM accumulators (N >= 1024, else nullptr)
   void (*br_tx)(const BrArgs);       // block-per-gate, second transform exchange through TMEM (N = 1024, else nullptr)
   void (*br_txs)(const BrArgs);      // same + key rows TMA-staged through shared memory
+  void (*br_tms)(const BrArgs);      // TMEM accumulators + TMA-staged key rows + single exchange buffer: 6 blocks/SM (N = 1024)
+  size_t (*br_tms_smem)(int n);
+  void (*br_mg)(const BrArgs, long long);  // G gates per block sharing one staged copy of the key rows, TMEM accumulators (N = 1024)
+  size_t (*br_mg_smem)(int n);
 };
+#ifndef TFHE_BR_MG_G
+#define TFHE_BR_MG_G 6
+#endif
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto mg_kernel() -> void (*)(const BrArgs, long long) {
+  if constexpr (LOGN == 10) return blind_rotate_mg_kernel<LOGN, L, BG, SMALL, TFHE_BR_MG_G>;
+  else return nullptr;
+}
+template <int LOGN> size_t br_mg_smem(int n) { return br_mg_smem_bytes<LOGN, TFHE_BR_MG_G>(n); }
+#ifndef TFHE_BR_TMS_MINB
+#define TFHE_BR_TMS_MINB 6
+#endif
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto tms_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10) return blind_rotate_tms_kernel<LOGN, L, BG, SMALL, TFHE_BR_TMS_MINB>;
+  else return nullptr;
+}
+template <int LOGN> size_t br_tms_smem(int n) { return br_tms_smem_bytes<LOGN>(n); }
 template <int LOGN> size_t br_smem(int n) { return br_smem_bytes<LOGN>(n); }
 template <int LOGN> size_t br_staged_smem(int n) { return br_staged_smem_bytes<LOGN>(n); }
 #ifndef TFHE_BR_W16_MINB
@@ -195,7 +219,8 @@ constexpr auto tm_kernel() -> void (*)(const BrArgs) {
     blind_rotate_kernel<LOGN, L, BG, SMALL, MINB, true>,                                            \
     blind_rotate_staged_kernel<LOGN, L, BG, SMALL, MINBS>, cmux_kernel<LOGN, L, BG, SMALL, MINB>,   \
     br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>(),           \
-    tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>() }
+    tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>(), tms_kernel<LOGN, L, BG, SMALL>(), br_tms_smem<LOGN>,  \
+    mg_kernel<LOGN, L, BG, SMALL>(), br_mg_smem<LOGN> }
 #ifndef TFHE_BR_MINB_N1024
 #define TFHE_BR_MINB_N1024 4
 #endif
@@ -245,6 +270,9 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   a.bsk_tex = c->bsk_tex;
   if (c->br_variant == 6 && V.br_txs) V.br_txs<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 5 && V.br_tx) V.br_tx<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  else if (c->br_variant == 8 && V.br_mg)
+    V.br_mg<<<(unsigned)((count + TFHE_BR_MG_G - 1) / TFHE_BR_MG_G), TFHE_BR_MG_G * T, V.br_mg_smem(c->P.n), s>>>(a, (long long)count);
+  else if (c->br_variant == 7 && V.br_tms) V.br_tms<<<(unsigned)count, T, V.br_tms_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 4 && V.br_tm) V.br_tm<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 1) V.br_staged<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 2) V.br_tex<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
@@ -423,6 +451,10 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
   const Variant& V = kVariants[v];
+  if (V.br_mg && (e = cudaFuncSetAttribute(V.br_mg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_mg_smem(2048))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_mg)", e);
+  if (V.br_tms && (e = cudaFuncSetAttribute(V.br_tms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_tms_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_tms)", e);
   if (V.br_tm && (e = cudaFuncSetAttribute(V.br_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tm)", e);
   if (V.br_tx && (e = cudaFuncSetAttribute(V.br_tx, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
@@ -458,7 +490,7 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
   if (const char* sel = getenv("TFHE_B200_BR"))
-    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
   if ((e = cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KSM_SMEM)) != cudaSuccess)
@@ -1018,7 +1050,9 @@ int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
 
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;
-  if (variant < 0 || variant > 6) return fail(c, TFHE_ERR_ARG, "variant must be 0 (ldg), 1 (tma), 2 (tex), 3 (w16), 4 (tmem), 5 (tmex) or 6 (tmex+tma)");
+  if (variant < 0 || variant > 8) return fail(c, TFHE_ERR_ARG, "variant must be 0 (ldg), 1 (tma), 2 (tex), 3 (w16), 4 (tmem), 5 (tmex), 6 (tmex+tma), 7 (tms) or 8 (mg)");
+  if (variant == 8 && (!kVariants[c->variant].br_mg || c->P.n > 2048)) return fail(c, TFHE_ERR_ARG, "the gates-per-block kernel exists for N = 1024, n <= 2048 only");
+  if (variant == 7 && !kVariants[c->variant].br_tms) return fail(c, TFHE_ERR_ARG, "the six-blocks-per-SM kernel exists for N = 1024 only");
   if (variant >= 5 && !kVariants[c->variant].br_tx) return fail(c, TFHE_ERR_ARG, "the TMEM-exchange kernel exists for N = 1024 only");
   if (variant == 4 && !kVariants[c->variant].br_tm) return fail(c, TFHE_ERR_ARG, "the TMEM-accumulator kernel needs N >= 1024");
   if (variant == 3 && !kVariants[c->variant].br_w16) return fail(c, TFHE_ERR_ARG, "the warp-per-gate kernel exists for N = 1024 only");

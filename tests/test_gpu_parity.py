@@ -75,7 +75,8 @@ def test_key_fetch_variants_agree(O, gpu, name):
     """The three ways the kernel can read key rows (LDG from L2, TMA-staged shared memory, texture pipe) run the same
     arithmetic in the same order: outputs are bit-identical to each other (and, at 80-bit, to the oracle)."""
     P, sk, ck, ctx = gpu(name)
-    ct = sk.encrypt_bool([0, 1, 1], 5) if name == "80" else sk.encrypt_message([3, 17, 30], 32, 5)
+    ct = sk.encrypt_bool([0, 1, 1, 0, 1, 0, 0, 1], 5) if name == "80" else sk.encrypt_message([3, 17, 30], 32, 5)
+    ct[1, 3] = ct[1, 4] = ct[2, 0] = 0  # mask words that round to X^0: the skipped-step paths (differ per gate of a shared block)
     outs = {}
     try:
         for v in ("ldg", "tma", "tex"):
@@ -88,6 +89,10 @@ def test_key_fetch_variants_agree(O, gpu, name):
             outs["tmex"] = ctx.blind_rotate_batch(ct)
             ctx.set_blind_rotate_variant("tmex+tma")
             outs["tmex+tma"] = ctx.blind_rotate_batch(ct)
+            ctx.set_blind_rotate_variant("tms")  # 6 blocks/SM: TMEM accumulators + TMA-staged key rows, 158 registers
+            outs["tms"] = ctx.blind_rotate_batch(ct)
+            ctx.set_blind_rotate_variant("mg")   # 6 gates per block sharing one staged copy of the key rows (8 gates: one full + one partial block)
+            outs["mg"] = ctx.blind_rotate_batch(ct)
         ctx.set_blind_rotate_variant("tmem")  # block-per-gate kernel with the accumulators in TMEM
         outs["tmem"] = ctx.blind_rotate_batch(ct)
     finally:
@@ -96,11 +101,12 @@ def test_key_fetch_variants_agree(O, gpu, name):
     if "w16" in outs:
         assert np.array_equal(outs["ldg"], outs["w16"])
         assert np.array_equal(outs["ldg"], outs["tmex"]) and np.array_equal(outs["ldg"], outs["tmex+tma"])
+        assert np.array_equal(outs["ldg"], outs["tms"]) and np.array_equal(outs["ldg"], outs["mg"])
     assert np.array_equal(outs["ldg"], outs["tmem"])
     if name == "80":
         ev = O.Evaluator(P.N)
         want = np.stack([ev.blind_rotate(P, c, ck.testvec, ck.bsk_fft, ck.offset) for c in ct])
-        assert np.array_equal(outs["ldg"].reshape(3, -1), want)
+        assert np.array_equal(outs["ldg"].reshape(len(ct), -1), want)
 
 
 def test_sample_extract_and_key_switch_bit_exact(O, gpu):  # rows a16, a17

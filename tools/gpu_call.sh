@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 tools/bench_c5_multi.py > gpurun_out/c24_c5_n8.txt 2>&1; tail -2 gpurun_out/c24_c5_n8.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/c24_bench_n4.txt 2>&1; tail -1 gpurun_out/c24_bench_n4.txt | cut -c1-300
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "variants_agree" > gpurun_out/c29_pytest.txt 2>&1; tail -3 gpurun_out/c29_pytest.txt
+timeout 300 compute-sanitizer --tool racecheck python tools/sanitize.py --variant=mg > gpurun_out/c29_race_mg.txt 2>&1; grep -v "^=========     " gpurun_out/c29_race_mg.txt | tail -4
+TFHE_B200_BR=mg timeout 120 python tools/gpu_quick.py 128 4096 2>&1 | tail -2
