@@ -279,6 +279,45 @@ def test_full_size_batch_properties(T, gpu):
     assert np.array_equal(got[0], got[4095])
 
 
+def test_full_size_adder_circuits_config3(T, O, gpu):
+    """BASELINE config 3 size: 8-bit ripple-carry adder x 1024 instances (40 960 bootstraps in 17 dependent levels, every
+    level's key switch on the tensor-core path with the job -> wire scatter) — every sum must equal (x + y) mod 256, and
+    instance 0, re-run alone through the small-batch path (row-gather key switch), must give the very same words."""
+    P, sk, ck, ctx = gpu("128")
+    bits, inst = 8, 1024
+    rng = np.random.default_rng(14)
+    x, y = rng.integers(0, 1 << bits, inst), rng.integers(0, 1 << bits, inst)
+    circ = T.circuit.ripple_carry_adder(bits)
+    assert circ.n_bootstraps == 40
+    ins = np.stack([sk.encrypt_bool((x >> i) & 1, 500 + i) for i in range(bits)] +
+                   [sk.encrypt_bool((y >> i) & 1, 600 + i) for i in range(bits)])
+    cst = np.broadcast_to(O.constant(P, False), (1, inst, P.n + 1))
+    wires = np.concatenate([ins, cst])
+    got = ctx.circuit_run(circ.gates, 2 * bits + 1, wires, circ.out_wires)
+    s = sum(sk.decrypt_bool(got[i]).astype(np.int64) << i for i in range(bits))
+    assert np.array_equal(s, (x + y) % (1 << bits))
+    one = ctx.circuit_run(circ.gates, 2 * bits + 1, np.ascontiguousarray(wires[:, :1]), circ.out_wires)
+    assert np.array_equal(one[:, 0], got[:, 0])
+
+
+def test_full_size_pbs_config4(T, O, gpu):
+    """BASELINE config 4 size: programmable bootstrap, Uint5 (n = 1071, N = 2048, msgMod 32), batch 2048 with a different
+    LUT per ciphertext (identity, x mod 16, x >= 16: examples/add_two_numbers/main.go:59-72) — decoded outputs exact."""
+    P, sk, ck, ctx = gpu("uint5")
+    m, count = 32, 2048
+    rng = np.random.default_rng(15)
+    msgs = rng.integers(0, m, count)
+    ct = sk.encrypt_message(msgs, m, 77)
+    fs = [lambda v: v, lambda v: v % 16, lambda v: int(v >= 16)]
+    luts = np.stack([O.gen_lut(P, m, f) for f in fs])
+    sel = rng.integers(0, 3, count)
+    got = ctx.bootstrap_batch(ct, luts[sel])
+    want = np.array([fs[k](int(v)) for k, v in zip(sel, msgs)])
+    assert np.array_equal(sk.decrypt_message(got, m), want)
+    same = ctx.bootstrap_batch(ct[:3], luts[sel[:3]])   # batch position must not matter
+    assert np.array_equal(same, got[:3])
+
+
 def test_circuit_full_adder_and_ripple_carry_bit_exact(T, O, gpu):
     """Levelised circuit runner (tfhe_circuit_run) == the reference's gate-by-gate evaluation (README.md:78-114):
     every wire is produced by the same gates.X arithmetic, so outputs are bit-identical to chaining single gates."""
