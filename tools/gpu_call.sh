@@ -1,2 +1,3 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q --durations=5 > gpurun_out/c30_pytest.txt 2>&1; tail -14 gpurun_out/c30_pytest.txt
+( VARIANTS="" bash tools/exp_variants.sh ) > gpurun_out/c31_variants.txt 2>&1
+grep "^==\|^BR\|correct" gpurun_out/c31_variants.txt | cut -c1-200
