@@ -197,3 +197,34 @@ def test_pbs_uint_sets(O, keyset, name, m):  # params/uint_params_test.go:61-126
     for f in (lambda x: x, lambda x: (m - 1) - x, lambda x: x % (m // 2)):
         got = sk.decrypt_message(O.bootstrap_batch(ck, ct, O.gen_lut(P, m, f)), m)
         assert list(got) == [f(x) for x in xs]
+
+
+def test_key_switch_as_byte_plane_contraction(O, keyset):
+    """The formulation behind the tensor-core key switch (go-tfhe_b200/csrc/key_switch_mma.cuh), modelled in numpy
+    against the oracle's trgsw/keyswitch.go:10-37: out = (0,..,0,b) - S @ KSK with S the 0/1 selection of the non-zero
+    digits (K = N*t*(base-1), kidx = (i*t + j)*(base-1) + (k-1)), evaluated as four u8 x u8 -> s32 products over the byte
+    planes of the key and recombined with shifts mod 2^32.  Any summation order gives the same words."""
+    P, sk, ck = keyset("80")
+    base, t, n, N = P.base, P.iks_t, P.n, P.N
+    rng = np.random.default_rng(21)
+    ext = rng.integers(0, 1 << 32, (3, N + 1), dtype=np.uint64).astype(np.uint32)
+    ext[1, :N] = 0
+    K = N * t * (base - 1)
+    ksk = ck.ksk.reshape(N, t, base, n + 1)
+    rows = ksk[:, :, 1:, :].reshape(K, n + 1)                       # k = 0 rows dropped: kidx order
+    planes = np.stack([(rows >> (8 * p)) & 0xFF for p in range(4)]).astype(np.int64)   # [4][K][n+1], values < 256
+    prec = np.uint32(1 << (32 - (1 + P.basebit * t)))
+    for g in range(len(ext)):
+        abar = ext[g, :N] + prec
+        S = np.zeros(K, dtype=np.int64)
+        for j in range(t):
+            k = (abar >> np.uint32(32 - (j + 1) * P.basebit)) & np.uint32(base - 1)
+            i = np.nonzero(k)[0]
+            S[(i * t + j) * (base - 1) + (k[i].astype(np.int64) - 1)] = 1
+        assert S.sum() <= N * t
+        D = np.einsum("k,pkw->pw", S, planes)                       # four exact integer products, each < 2^31
+        assert D.max() < (1 << 31)
+        total = sum(D[p] << (8 * p) for p in range(4)) & 0xFFFFFFFF
+        out = (-total) & 0xFFFFFFFF
+        out[n] = (out[n] + int(ext[g, N])) & 0xFFFFFFFF
+        assert np.array_equal(out.astype(np.uint32), O.key_switch(P, ext[g], ck.ksk))
