@@ -125,7 +125,7 @@ __global__ void sample_extract_kernel(const uint32_t* __restrict__ trlwe, uint32
 // ksk rows are padded to `stride` words (multiple of 4) for 16-byte loads.  Row order is the
 // reference's: (base*t*i + base*j + k).  Subtractions commute mod 2^32, so any order is bit-exact.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) key_switch_kernel(const uint32_t* __restrict__ lwe_in,
+__global__ void __launch_bounds__(512) key_switch_kernel(const uint32_t* __restrict__ lwe_in,
                                                          const uint32_t* __restrict__ ksk,
                                                          uint32_t* __restrict__ out, int N, int n, int basebit,
                                                          int t, int stride, const GateDesc* __restrict__ out_gates,

@@ -360,7 +360,10 @@ int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32
     return launch_key_switch_mma(c, count, d_lwe1, d_out, s, out_gates, instances);
   const size_t sm = (size_t)c->P.N * c->P.iks_t * sizeof(uint32_t);
   if (sm > 128 * 1024) return fail(c, TFHE_ERR_ARG, "N * iks_t too large for the key-switch kernel");
-  key_switch_kernel<<<(unsigned)count, 256, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
+  // one thread per 16-byte column of a key row, so that the row loop runs once (n = 1071: 268 columns -> 288 threads,
+  // not 256 + a second pass with 12 live threads)
+  const int ks_threads = std::min(512, std::max(128, (c->ksk_stride / 4 + 31) / 32 * 32));
+  key_switch_kernel<<<(unsigned)count, ks_threads, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
                                                      c->P.iks_t, c->ksk_stride, out_gates, instances);
   c->launches++;
   CK(c, cudaGetLastError());
