@@ -181,7 +181,7 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
  * block sharing one double-buffered staged copy of the key rows (N = 1024).  All compute identical results;
  * the default is the fastest measured (profiles/r01_experiments.md). */
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
-/* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default), 1 = one block per
+/* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default: the contraction wherever it exists), 1 = one block per
  * ciphertext gathering its N*t*(1-1/base) key rows out of L2, 2 = the whole batch as one exact u8 x u8 -> s32
  * contraction on the tensor cores (tcgen05.mma kind::i8 over the byte planes of the key; basebit = 2 parameter sets
  * only).  Both are bit-identical: additions mod 2^32 commute. */
