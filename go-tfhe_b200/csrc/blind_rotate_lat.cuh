@@ -1,0 +1,138 @@
+// blind_rotate_lat.cuh — latency-oriented blind rotation for SMALL batches (variant "lat").
+//
+// The throughput kernel (blind_rotate.cuh) gives one gate two warps and relies on four co-resident gates per SM; a batch
+// that does not even fill the SMs (a single gates.NAND call — BASELINE config 1 — or a narrow circuit level) leaves the
+// machine idle while every gate walks its 6 forward + 2 inverse transforms per step one after the other.  Here a gate
+// gets FOUR warps in two groups that work concurrently on the two polynomials of the accumulator:
+//   group p (64 threads):  digits of polynomial p -> L forward transforms -> multiply-accumulate with rows p*L .. p*L+L-1
+//                          into partial spectra for BOTH outputs                     (evaluator/evaluator.go:50-81)
+//   exchange:              group 0 hands its partial B spectrum to group 1 and receives group 1's partial A spectrum
+//   group p:               inverse transform of output p, rounding, accumulator update (poly/fourier_transform.go:88-125)
+// so a step costs L forward + 1 inverse transform of latency instead of 2L + 2.  The partial sums are added in a
+// different order than the reference's row-by-row accumulation, which is immaterial exactly where this kernel is
+// enabled: the parameter sets whose rounded result is the exact integer result (SMALL: 80/110/128-bit; DESIGN.md
+// section 2) — outputs are bit-identical to the default kernel and the oracle there.
+#pragma once
+#include "blind_rotate.cuh"
+
+namespace tfhe {
+
+template <int LOGN>
+constexpr size_t br_lat_smem_bytes(int n) {
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * 2 * (1 << (LOGN - 1)) * 16 /*exchange: 2 groups x 2 buffers*/ +
+         (size_t)2 * (1 << (LOGN - 1)) * 16 /*partial spectra crossing between the groups*/ +
+         (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
+}
+
+template <int LOGN, int L, int BGBIT, bool SMALL>
+__global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_kernel(const BrArgs A) {
+  static_assert(SMALL, "partial sums are reordered: exact parameter sets only");
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                              // [2][N]
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);                         // [2 groups][2][M]
+  double2* cross = reinterpret_cast<double2*>(smem_raw + 8 * N + 64 * M);             // [2][M]: [p] is read by group p
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 64 * M + 32 * M);
+  const int grp = threadIdx.x / T, tau = threadIdx.x % T;
+  const long long g = blockIdx.x;
+  const int n = A.n;
+  const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+
+  for (int i = threadIdx.x; i < n; i += 2 * T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
+  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
+  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
+  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+  for (int j = threadIdx.x; j < N; j += 2 * T) {
+    const int idx = (j - btil) & (2 * N - 1);
+    const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
+    acc[j] = (idx & N) ? ~va : va;
+    acc[N + j] = (idx & N) ? ~vb : vb;
+  }
+  Fft<LOGN - 1, false, true> fft;
+  fft.init(ex + (size_t)grp * 2 * M, A.tw_tab, tau);
+  fft.bar_id = 1 + grp;
+  __syncthreads();
+
+  const size_t row_stride = (size_t)2 * L * 2 * M;
+  uint32_t* P = acc + grp * N;  // the polynomial this group decomposes AND the one it updates
+  for (int i = 0; i < n; i++) {
+    const int at = abar[i];
+    if (at == 0) continue;  // uniform over the block
+    const double2* __restrict__ bk = A.bsk + row_stride * i + tau;
+    double2 accA[8], accB[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
+    uint32_t dre[8], dim[8];
+    const int ib = (tau - at) & (2 * N - 1);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      dre[a] = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
+      dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
+    }
+#pragma unroll 1
+    for (int lvl = 0; lvl < L; lvl++) {
+      const int sh = 32 - (lvl + 1) * BGBIT;
+      double2 x[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
+        x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+      }
+      fft.forward(x, A.tw0);
+      const double2* __restrict__ rowA = bk + (size_t)((grp * L + lvl) * 2) * M;
+      const double2* __restrict__ rowB = rowA + M;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const double2 ka = __ldg(rowA + e * T);
+        const double2 kb = __ldg(rowB + e * T);
+        accA[e].x = fma(x[e].x, ka.x, accA[e].x);
+        accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
+        accA[e].y = fma(x[e].x, ka.y, accA[e].y);
+        accA[e].y = fma(x[e].y, ka.x, accA[e].y);
+        accB[e].x = fma(x[e].x, kb.x, accB[e].x);
+        accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
+        accB[e].y = fma(x[e].x, kb.y, accB[e].y);
+        accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+      }
+    }
+    // hand the partial spectrum of the OTHER group's output across, keep and complete our own
+    if (grp == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) cross[M + e * T + tau] = accB[e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) cross[e * T + tau] = accA[e];
+    }
+    __syncthreads();
+    double2 y[8];
+    if (grp == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) { const double2 o = cross[e * T + tau]; y[e] = make_double2(accA[e].x + o.x, accA[e].y + o.y); }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; e++) { const double2 o = cross[M + e * T + tau]; y[e] = make_double2(accB[e].x + o.x, accB[e].y + o.y); }
+    }
+    fft.inverse(y, A.tw0);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      P[j] += to_torus<SMALL>(y[a].x);
+      P[j + M] += to_torus<SMALL>(y[a].y);
+    }
+    __syncthreads();  // both polynomials updated (and `cross` free) before the next step reads them
+  }
+
+  if (A.out_mode == 0) {
+    uint32_t* o = A.out + g * (2 * N);
+    for (int j = threadIdx.x; j < 2 * N; j += 2 * T) o[j] = acc[j];
+  } else {  // sample extract at 0 (trlwe_ops.go:10-21)
+    uint32_t* o = A.out + g * (N + 1);
+    for (int j = threadIdx.x; j < N; j += 2 * T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
+    if (threadIdx.x == 0) o[N] = acc[N];
+  }
+}
+
+}  // namespace tfhe

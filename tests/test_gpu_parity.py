@@ -79,9 +79,14 @@ def test_key_fetch_variants_agree(O, gpu, name):
     ct[1, 3] = ct[1, 4] = ct[2, 0] = 0  # mask words that round to X^0: the skipped-step paths (differ per gate of a shared block)
     outs = {}
     try:
-        for v in ("ldg", "tma", "tex"):
+        for v in ("throughput", "tma", "tex"):  # "throughput" = the default LDG kernel, never the small-batch latency kernel
             ctx.set_blind_rotate_variant(v)
-            outs[v] = ctx.blind_rotate_batch(ct)
+            outs["ldg" if v == "throughput" else v] = ctx.blind_rotate_batch(ct)
+        if name == "80":  # latency kernel (4 warps per gate, partial sums in a different order): exact sets only
+            ctx.set_blind_rotate_variant("lat")
+            outs["lat"] = ctx.blind_rotate_batch(ct)
+            ctx.set_blind_rotate_variant("ldg")  # default: picks the latency kernel by itself for this batch size
+            outs["auto"] = ctx.blind_rotate_batch(ct)
         if P.N == 1024:  # warp-per-gate kernel with TMEM accumulators: a different transform schedule, same exact result
             ctx.set_blind_rotate_variant("w16")
             outs["w16"] = ctx.blind_rotate_batch(ct)
@@ -103,6 +108,8 @@ def test_key_fetch_variants_agree(O, gpu, name):
         assert np.array_equal(outs["ldg"], outs["tmex"]) and np.array_equal(outs["ldg"], outs["tmex+tma"])
         assert np.array_equal(outs["ldg"], outs["tms"]) and np.array_equal(outs["ldg"], outs["mg"])
     assert np.array_equal(outs["ldg"], outs["tmem"])
+    if "lat" in outs:
+        assert np.array_equal(outs["ldg"], outs["lat"]) and np.array_equal(outs["ldg"], outs["auto"])
     if name == "80":
         ev = O.Evaluator(P.N)
         want = np.stack([ev.blind_rotate(P, c, ck.testvec, ck.bsk_fft, ck.offset) for c in ct])
