@@ -153,10 +153,15 @@ def test_bootstrap_bit_exact_and_decrypts(O, gpu, name):  # row a18
     P, sk, ck, ctx = gpu(name)
     bits = np.array([0, 1] * 8, dtype=np.uint8)
     ct = sk.encrypt_bool(bits, 123)
-    got = ctx.bootstrap_batch(ct)
+    got = ctx.bootstrap_batch(ct)              # default: the small-batch latency kernel for these sets
     want = O.bootstrap_batch(ck, ct)
     assert np.array_equal(got, want)
     assert list(sk.decrypt_bool(got)) == list(bits)
+    try:                                        # the throughput kernel (what large batches run) on the same inputs
+        ctx.set_blind_rotate_variant("throughput")
+        assert np.array_equal(ctx.bootstrap_batch(ct), want)
+    finally:
+        ctx.set_blind_rotate_variant("ldg")
 
 
 @pytest.mark.parametrize("name", ["80", "128"])
