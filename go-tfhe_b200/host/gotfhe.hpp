@@ -123,6 +123,22 @@ inline std::unique_ptr<CloudKey> NewCloudKey(const key::SecretKey& sk, uint64_t 
                         ck->BlindRotateTestvec.data(), ck->KeySwitchingKey.data(), ck->BootstrappingKey.data());
   return ck;
 }
+// cloudkey.NewCloudKey with the key material generated on the device (tfhe_ctx_generate_cloudkey): same fields, and the
+// engine that made them already holds the key, so no second upload happens.
+inline std::unique_ptr<CloudKey> NewCloudKeyOnDevice(const key::SecretKey& sk, uint64_t seed = 1, int device = 0) {
+  auto ck = std::make_unique<CloudKey>();
+  const params::Set& P = *sk.P;
+  ck->P = &P;
+  ck->BlindRotateTestvec.resize(2 * P.N);
+  ck->KeySwitchingKey.resize((size_t)P.ksk_rows() * (P.n + 1));
+  ck->BootstrappingKey.resize((size_t)P.n * 2 * P.L * 2 * P.N);
+  tfhe_params c = P.c();
+  if (tfhe_ctx_create(&c, device, &ck->ctx) != 0) throw std::runtime_error(std::string("tfhe_ctx_create: ") + tfhe_last_error(nullptr));
+  if (tfhe_ctx_generate_cloudkey(ck->ctx, sk.KeyLv0.data(), sk.KeyLv1.data(), P.alpha_lv0, P.alpha_lv1, seed, 1, &ck->DecompositionOffset,
+                                 ck->BootstrappingKey.data(), ck->KeySwitchingKey.data(), ck->BlindRotateTestvec.data()) != 0)
+    throw std::runtime_error(std::string("tfhe_ctx_generate_cloudkey: ") + tfhe_last_error(ck->ctx));
+  return ck;
+}
 }  // namespace cloudkey
 
 namespace lut {

@@ -37,6 +37,15 @@ int main(int argc, char** argv) {
     EXPECT(tlwe::DecryptLWEMessage(ev.BootstrapFunc(ct, [](int x) { return x; }, 2), 2, sk) == m, "identity(%d)", m);
     EXPECT(tlwe::DecryptLWEMessage(ev.BootstrapFunc(ct, [](int x) { return 1 - x; }, 2), 2, sk) == 1 - m, "not(%d)", m);
   }
+  {  // the same truth table with a cloud key generated on the device
+    auto dk = cloudkey::NewCloudKeyOnDevice(sk, 44);
+    for (int k = 0; k < 4; k++) {
+      bool a = k >> 1, b = k & 1;
+      auto r = gates::NAND(tlwe::EncryptBool(a, sk, seed++), tlwe::EncryptBool(b, sk, seed++), *dk);
+      EXPECT(tlwe::DecryptBool(r, sk) == !(a && b), "device key NAND(%d,%d)", a, b);
+    }
+    EXPECT(dk->DecompositionOffset == ck->DecompositionOffset && dk->BlindRotateTestvec == ck->BlindRotateTestvec, "device key constants");
+  }
   std::printf("%s: %d failures\n", P.name, failures);
   return failures ? 1 : 0;
 }
