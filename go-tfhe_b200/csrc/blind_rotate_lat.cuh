@@ -135,4 +135,134 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One group of N/16 threads per DIGIT (2L groups, 384 threads at L = 3): all 2L forward transforms of a CMUX step run
+// concurrently, every group writes its two partial products (digit spectrum x key row, for the A and the B output) to
+// shared memory, and the first group of each polynomial sums the 2L partials of "its" output in the reference's row order,
+// inverse-transforms and updates the accumulator.  One forward + one inverse transform of latency per step; the key rows
+// of the NEXT step are requested before the block barrier so that their L2 latency hides behind the inverse transform.
+// For batches of at most one gate per SM (variant "lat2"; same exactness condition as above).
+// ---------------------------------------------------------------------------------------------------------------
+template <int LOGN, int L>
+constexpr size_t br_lat2_smem_bytes(int n) {
+  // the partial products reuse the groups' exchange buffers (free once the forward transform is done), which keeps
+  // shared memory at ~105 KiB and leaves L1 room for the prefetched key rows of the next step (96 KiB)
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * L * 2 * (1 << (LOGN - 1)) * 16 /*exchange / partials: 2L groups x 2 buffers*/ +
+         (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
+}
+
+template <int LOGN, int L, int BGBIT, bool SMALL>
+__global__ void __launch_bounds__(2 * L * (1 << (LOGN - 4)), 1) blind_rotate_lat2_kernel(const BrArgs A) {
+  static_assert(SMALL, "partial sums are reordered: exact parameter sets only");
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8, NG = 2 * L;
+  static_assert(NG <= 15, "one named barrier per group");
+  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                                   // [2][N]
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);                              // [NG][2][M]
+  double2* part = ex;                                                                      // [NG][2 outputs][M], aliases ex
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + (size_t)NG * 32 * M);
+  const int grp = threadIdx.x / T, tau = threadIdx.x % T;
+  const int poly = grp / L, lvl = grp % L;
+  const long long g = blockIdx.x;
+  const int n = A.n;
+  const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+
+  for (int i = threadIdx.x; i < n; i += NG * T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
+  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
+  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
+  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+  for (int j = threadIdx.x; j < N; j += NG * T) {
+    const int idx = (j - btil) & (2 * N - 1);
+    const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
+    acc[j] = (idx & N) ? ~va : va;
+    acc[N + j] = (idx & N) ? ~vb : vb;
+  }
+  Fft<LOGN - 1, false, true> fft;
+  fft.init(ex + (size_t)grp * 2 * M, A.tw_tab, tau);
+  fft.bar_id = 1 + grp;
+  __syncthreads();
+
+  const size_t row_stride = (size_t)2 * L * 2 * M;
+  const int sh = 32 - (lvl + 1) * BGBIT;
+  uint32_t* P = acc + poly * N;  // the polynomial this group takes its digit from (and, for lvl == 0, the one it updates)
+  auto next_step = [&](int i) { while (i < n && abar[i] == 0) i++; return i; };  // X^0 steps are exact no-ops
+  auto prefetch_keys = [&](int i) {  // this group's 16 KiB of step i into L1: 128 lines, two per thread
+    const char* pf = reinterpret_cast<const char*>(A.bsk + row_stride * i + (size_t)(grp * 2) * M) + tau * 128;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
+  };
+  auto load_keys = [&](int i, double2 (&ka)[8], double2 (&kb)[8]) {
+    const double2* __restrict__ rowA = A.bsk + row_stride * i + (size_t)(grp * 2) * M + tau;
+    const double2* __restrict__ rowB = rowA + M;
+#pragma unroll
+    for (int e = 0; e < 8; e++) { ka[e] = __ldg(rowA + e * T); kb[e] = __ldg(rowB + e * T); }
+  };
+  double2 ka[8], kb[8];
+  int i = next_step(0);
+  if (i < n) load_keys(i, ka, kb);
+  while (i < n) {
+    const int at = abar[i];
+    const int inext = next_step(i + 1);
+    if (inext < n) prefetch_keys(inext);  // a whole step ahead of the loads that will want them
+    double2 x[8];
+    {
+      const int ib = (tau - at) & (2 * N - 1);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        const uint32_t wre = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
+        const uint32_t wim = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
+        x[a].x = field_to_double((wre >> sh) & MASK, BIAS);
+        x[a].y = field_to_double((wim >> sh) & MASK, BIAS);
+      }
+    }
+    fft.forward(x, A.tw0);
+    fft.group_barrier();  // every thread of the group has read the last exchange: both buffers are free for the partials
+    double2* pa = part + (size_t)(grp * 2) * M + tau;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      pa[e * T] = make_double2(fma(x[e].x, ka[e].x, -(x[e].y * ka[e].y)), fma(x[e].x, ka[e].y, x[e].y * ka[e].x));
+      pa[M + e * T] = make_double2(fma(x[e].x, kb[e].x, -(x[e].y * kb[e].y)), fma(x[e].x, kb[e].y, x[e].y * kb[e].x));
+    }
+    if (inext < n) load_keys(inext, ka, kb);  // L1 hits by now; in flight across the barrier and the inverse transform
+    __syncthreads();
+    if (lvl == 0) {  // groups 0 and L: output `poly` = sum over all 2L digits, in row order
+      double2 y[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) y[e] = part[(size_t)poly * M + e * T + tau];
+#pragma unroll
+      for (int r = 1; r < NG; r++) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const double2 o = part[(size_t)(r * 2 + poly) * M + e * T + tau];
+          y[e].x += o.x;
+          y[e].y += o.y;
+        }
+      }
+      // the inverse transform reuses this group's exchange buffers, which hold partials the OTHER summing group reads too
+      asm volatile("bar.sync %0, %1;" ::"n"(NG + 1), "n"(2 * T) : "memory");
+      fft.inverse(y, A.tw0);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        P[j] += to_torus<SMALL>(y[a].x);
+        P[j + M] += to_torus<SMALL>(y[a].y);
+      }
+    }
+    __syncthreads();  // both polynomials updated and `part` free before the next step
+    i = inext;
+  }
+
+  if (A.out_mode == 0) {
+    uint32_t* o = A.out + g * (2 * N);
+    for (int j = threadIdx.x; j < 2 * N; j += NG * T) o[j] = acc[j];
+  } else {
+    uint32_t* o = A.out + g * (N + 1);
+    for (int j = threadIdx.x; j < N; j += NG * T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
+    if (threadIdx.x == 0) o[N] = acc[N];
+  }
+}
+
 }  // namespace tfhe

@@ -164,7 +164,15 @@ struct Variant {
   size_t (*br_mg_smem)(int n);
   void (*br_lat)(const BrArgs);      // latency mode: 4 warps per gate, the two polynomials in parallel (exact sets, N = 1024)
   size_t (*br_lat_smem)(int n);
+  void (*br_lat2)(const BrArgs);     // latency mode, one group per digit (2L x N/16 threads): <= 1 gate per SM
+  size_t (*br_lat2_smem)(int n);
 };
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto lat2_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10 && SMALL) return blind_rotate_lat2_kernel<LOGN, L, BG, SMALL>;
+  else return nullptr;
+}
+template <int LOGN, int L> size_t br_lat2_smem(int n) { return br_lat2_smem_bytes<LOGN, L>(n); }
 template <int LOGN, int L, int BG, bool SMALL>
 constexpr auto lat_kernel() -> void (*)(const BrArgs) {
   if constexpr (LOGN == 10 && SMALL) return blind_rotate_lat_kernel<LOGN, L, BG, SMALL>;
@@ -230,7 +238,8 @@ constexpr auto tm_kernel() -> void (*)(const BrArgs) {
     blind_rotate_staged_kernel<LOGN, L, BG, SMALL, MINBS>, cmux_kernel<LOGN, L, BG, SMALL, MINB>,   \
     br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>(),           \
     tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>(), tms_kernel<LOGN, L, BG, SMALL>(), br_tms_smem<LOGN>,  \
-    mg_kernel<LOGN, L, BG, SMALL>(), br_mg_smem<LOGN>, lat_kernel<LOGN, L, BG, SMALL>(), br_lat_smem<LOGN> }
+    mg_kernel<LOGN, L, BG, SMALL>(), br_mg_smem<LOGN>, lat_kernel<LOGN, L, BG, SMALL>(), br_lat_smem<LOGN>,  \
+    lat2_kernel<LOGN, L, BG, SMALL>(), br_lat2_smem<LOGN, L> }
 #ifndef TFHE_BR_MINB_N1024
 #define TFHE_BR_MINB_N1024 4
 #endif
@@ -280,6 +289,9 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   a.bsk_tex = c->bsk_tex;
   if (c->br_variant == 6 && V.br_txs) V.br_txs<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 5 && V.br_tx) V.br_tx<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
+  // latency mode with one 64-thread group per digit (2L groups): explicit choice only
+  else if (V.br_lat2 && c->br_variant == 11)  // measured: not faster than the two-group kernel below, so never picked automatically
+    V.br_lat2<<<(unsigned)count, 2 * c->P.L * T, V.br_lat2_smem(c->P.n), s>>>(a);
   // latency mode: a batch that cannot fill the SMs with the throughput kernel (<= 2 gates per SM) gets four warps per gate
   else if (V.br_lat && (c->br_variant == 9 || (c->br_variant == 0 && c->br_auto_lat && count <= 2 * (int64_t)c->sm_count)))
     V.br_lat<<<(unsigned)count, 2 * T, V.br_lat_smem(c->P.n), s>>>(a);
@@ -468,6 +480,8 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
   const Variant& V = kVariants[v];
+  if (V.br_lat2 && (e = cudaFuncSetAttribute(V.br_lat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat2_smem(2048))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_lat2)", e);
   if (V.br_lat && (e = cudaFuncSetAttribute(V.br_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_lat)", e);
   if (V.br_mg && (e = cudaFuncSetAttribute(V.br_mg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_mg_smem(2048))) != cudaSuccess)
@@ -509,7 +523,7 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
   if (const char* sel = getenv("TFHE_B200_BR"))
-    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat") ? 9 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat") ? 9 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
   if (c->br_variant == 10) { c->br_variant = 0; c->br_auto_lat = false; }
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
@@ -1071,6 +1085,10 @@ int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;
   if (variant == 10) { c->br_variant = 0; c->br_auto_lat = false; return TFHE_OK; }  // throughput kernel at every batch size
+  if (variant == 11) {
+    if (!kVariants[c->variant].br_lat2 || c->P.n > 2048) return fail(c, TFHE_ERR_ARG, "the per-digit latency kernel exists for the exact N = 1024 sets only");
+    c->br_variant = 11; c->br_auto_lat = true; return TFHE_OK;
+  }
   if (variant < 0 || variant > 9) return fail(c, TFHE_ERR_ARG, "variant must be 0 (default), 1 (tma), 2 (tex), 3 (w16), 4 (tmem), 5 (tmex), 6 (tmex+tma), 7 (tms), 8 (mg), 9 (lat) or 10 (ldg at every batch size)");
   if (variant == 9 && !kVariants[c->variant].br_lat) return fail(c, TFHE_ERR_ARG, "the latency kernel exists for the exact N = 1024 sets only");
   c->br_auto_lat = true;

@@ -180,7 +180,8 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
  * in tensor memory + key rows TMA-staged into one shared-memory buffer, 158 registers (N = 1024), 8 = six gates per
  * block sharing one double-buffered staged copy of the key rows (N = 1024), 9 = latency mode: four warps per gate, the
  * two polynomials of a CMUX step in parallel (80/110/128-bit sets; variant 0 switches to it on its own for batches of at
- * most two gates per SM), 10 = variant 0 without that switch.  All compute identical results;
+ * most two gates per SM), 10 = variant 0 without that switch, 11 = latency mode with one 64-thread group per digit (2L
+ * groups; measured no faster than 9, explicit choice only).  All compute identical results;
  * the default is the fastest measured (profiles/r01_experiments.md). */
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
 /* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default: the contraction wherever it exists), 1 = one block per

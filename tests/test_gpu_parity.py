@@ -85,7 +85,9 @@ def test_key_fetch_variants_agree(O, gpu, name):
         if name == "80":  # latency kernel (4 warps per gate, partial sums in a different order): exact sets only
             ctx.set_blind_rotate_variant("lat")
             outs["lat"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("ldg")  # default: picks the latency kernel by itself for this batch size
+            ctx.set_blind_rotate_variant("lat2")  # one 64-thread group per digit
+            outs["lat2"] = ctx.blind_rotate_batch(ct)
+            ctx.set_blind_rotate_variant("ldg")  # default: picks a latency kernel by itself for this batch size
             outs["auto"] = ctx.blind_rotate_batch(ct)
         if P.N == 1024:  # warp-per-gate kernel with TMEM accumulators: a different transform schedule, same exact result
             ctx.set_blind_rotate_variant("w16")
@@ -110,6 +112,7 @@ def test_key_fetch_variants_agree(O, gpu, name):
     assert np.array_equal(outs["ldg"], outs["tmem"])
     if "lat" in outs:
         assert np.array_equal(outs["ldg"], outs["lat"]) and np.array_equal(outs["ldg"], outs["auto"])
+        assert np.array_equal(outs["ldg"], outs["lat2"])
     if name == "80":
         ev = O.Evaluator(P.N)
         want = np.stack([ev.blind_rotate(P, c, ck.testvec, ck.bsk_fft, ck.offset) for c in ct])
