@@ -21,6 +21,7 @@ template <int LOGN>
 constexpr size_t br_lat_smem_bytes(int n) {
   return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * 2 * (1 << (LOGN - 1)) * 16 /*exchange: 2 groups x 2 buffers*/ +
          (size_t)2 * (1 << (LOGN - 1)) * 16 /*partial spectra crossing between the groups*/ +
+         (size_t)2 * 2 * (1 << (LOGN - 1)) * 16 /*key rows of the next digit, one private slot set per thread*/ +
          (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
 }
 
@@ -34,11 +35,24 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                              // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);                         // [2 groups][2][M]
   double2* cross = reinterpret_cast<double2*>(smem_raw + 8 * N + 64 * M);             // [2][M]: [p] is read by group p
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 64 * M + 32 * M);
+  double2* stage = reinterpret_cast<double2*>(smem_raw + 8 * N + 64 * M + 32 * M);    // [2 groups][16][T]
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 64 * M + 32 * M + 64 * M);
   const int grp = threadIdx.x / T, tau = threadIdx.x % T;
   const long long g = blockIdx.x;
   const int n = A.n;
   const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+  // The 16 key values a thread multiplies with are copied asynchronously (cp.async, SASS LDGSTS) into 16 shared-memory
+  // slots that only this thread reads, one digit ahead: with a single gate on the SM nothing else hides the L2 latency
+  // of the key rows, and no registers are held in flight.  Thread-private slots need no barrier, only wait_group.
+  double2* my_stage = stage + (size_t)grp * 16 * T + tau;
+  auto stage_keys = [&](const double2* rowA) {  // rowA already offset by tau; the B row follows M elements later
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + e * T)), "l"(rowA + e * T) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (8 + e) * T)), "l"(rowA + M + e * T) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
   for (int i = threadIdx.x; i < n; i += 2 * T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
   const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
@@ -57,10 +71,15 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
 
   const size_t row_stride = (size_t)2 * L * 2 * M;
   uint32_t* P = acc + grp * N;  // the polynomial this group decomposes AND the one it updates
+  int staged = -1;              // step whose first digit is already on its way into the stage
   for (int i = 0; i < n; i++) {
     const int at = abar[i];
     if (at == 0) continue;  // uniform over the block
     const double2* __restrict__ bk = A.bsk + row_stride * i + tau;
+    if (staged != i) {  // first step, or the one after a skipped step: drop whatever is in flight, then stage the right rows
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      stage_keys(bk + (size_t)(grp * L * 2) * M);
+    }
     double2 accA[8], accB[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
@@ -82,20 +101,23 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
         x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
       }
       fft.forward(x, A.tw0);
-      const double2* __restrict__ rowA = bk + (size_t)((grp * L + lvl) * 2) * M;
-      const double2* __restrict__ rowB = rowA + M;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      double2 ka[8], kb[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) { ka[e] = my_stage[e * T]; kb[e] = my_stage[(8 + e) * T]; }
+      // next digit of this group: next level, or the first level of the next step (row-sets are contiguous; the key
+      // buffer has slack past the last step) — its L2 latency hides behind the next transform(s)
+      stage_keys(bk + ((lvl + 1 < L) ? (size_t)((grp * L + lvl + 1) * 2) * M : row_stride + (size_t)(grp * L * 2) * M));
 #pragma unroll
       for (int e = 0; e < 8; e++) {
-        const double2 ka = __ldg(rowA + e * T);
-        const double2 kb = __ldg(rowB + e * T);
-        accA[e].x = fma(x[e].x, ka.x, accA[e].x);
-        accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
-        accA[e].y = fma(x[e].x, ka.y, accA[e].y);
-        accA[e].y = fma(x[e].y, ka.x, accA[e].y);
-        accB[e].x = fma(x[e].x, kb.x, accB[e].x);
-        accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
-        accB[e].y = fma(x[e].x, kb.y, accB[e].y);
-        accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+        accA[e].x = fma(x[e].x, ka[e].x, accA[e].x);
+        accA[e].x = fma(-x[e].y, ka[e].y, accA[e].x);
+        accA[e].y = fma(x[e].x, ka[e].y, accA[e].y);
+        accA[e].y = fma(x[e].y, ka[e].x, accA[e].y);
+        accB[e].x = fma(x[e].x, kb[e].x, accB[e].x);
+        accB[e].x = fma(-x[e].y, kb[e].y, accB[e].x);
+        accB[e].y = fma(x[e].x, kb[e].y, accB[e].y);
+        accB[e].y = fma(x[e].y, kb[e].x, accB[e].y);
       }
     }
     // hand the partial spectrum of the OTHER group's output across, keep and complete our own
@@ -123,7 +145,9 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
       P[j + M] += to_torus<SMALL>(y[a].y);
     }
     __syncthreads();  // both polynomials updated (and `cross` free) before the next step reads them
+    staged = i + 1;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 
   if (A.out_mode == 0) {
     uint32_t* o = A.out + g * (2 * N);
