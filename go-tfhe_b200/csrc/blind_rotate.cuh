@@ -66,7 +66,11 @@
 #ifndef TFHE_BR_WARP_EX
 #define TFHE_BR_WARP_EX 0       // 1: exchanges whose 8-thread groups lie inside one warp use a third buffer and __syncwarp instead of a block barrier
 #endif
-#define TFHE_BR_NBUF (TFHE_BR_WARP_EX ? 3 : 2)
+#ifndef TFHE_BR_WARP_EX_LOGN
+#define TFHE_BR_WARP_EX_LOGN 11 // ... and always from this ring size on (4-warp blocks: measured +2.6 % at N = 2048, -9 % at N = 1024)
+#endif
+__host__ __device__ constexpr bool br_warp_ex(int logn) { return TFHE_BR_WARP_EX || logn >= TFHE_BR_WARP_EX_LOGN; }
+__host__ __device__ constexpr int br_nbuf(int logn) { return br_warp_ex(logn) ? 3 : 2; }  // exchange buffers per transform group
 #define TFHE_PRAGMA_(x) _Pragma(#x)
 #define TFHE_UNROLL(n) TFHE_PRAGMA_(unroll n)
 
@@ -284,7 +288,7 @@ struct Fft {
     double2* buf = ex;
     // threads that trade points in this exchange: stride(coarser pass) consecutive threads; inside one warp for the
     // exchanges next to the last pass (8 threads at N = 1024, 16 at N = 2048)
-    constexpr bool WARP_LOCAL = TFHE_BR_WARP_EX && !SINGLE && (G::stride(KW < KR ? KW : KR) <= 32) && (G::T % 32 == 0);
+    constexpr bool WARP_LOCAL = br_warp_ex(LOGM + 1) && !SINGLE && !NAMED && (G::stride(KW < KR ? KW : KR) <= 32) && (G::T % 32 == 0);
     if constexpr (SINGLE) {
       mbar_wait(rd_bar, rd_phase);  // every thread has finished reading the previous exchange
       rd_phase ^= 1u;
@@ -647,7 +651,7 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
 
 template <int LOGN>
 constexpr size_t br_smem_bytes(int n) {
-  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)TFHE_BR_NBUF * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [NBUF][EXW][M]*/ +
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)br_nbuf(LOGN) * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [NBUF][EXW][M]*/ +
          (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
 }
 
@@ -667,7 +671,7 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][EXW][M]
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * TFHE_BR_NBUF * TFHE_BR_EXW * M);
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M);
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   const int n = A.n;
@@ -959,7 +963,7 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const Cmu
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);       // holds ct0, becomes the result
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);
-  uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 16 * TFHE_BR_NBUF * TFHE_BR_EXW * M);  // [2][N]
+  uint32_t* c1 = reinterpret_cast<uint32_t*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M);  // [2][N]
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   for (int j = tau; j < 2 * N; j += T) {

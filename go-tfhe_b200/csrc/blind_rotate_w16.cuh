@@ -430,7 +430,7 @@ __global__ void TFHE_BR_TM_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_tm_kerne
   __shared__ uint32_t s_tmem_base;
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][EXW][M]
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * TFHE_BR_NBUF * TFHE_BR_EXW * M);
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M);
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   const int n = A.n;

@@ -678,7 +678,7 @@ int tfhe_ctx_generate_cloudkey(tfhe_ctx* c, const uint32_t* key_lv0, const uint3
     a.seed = seed; a.L = P.L; a.bgbit = P.bgbit; a.tw0 = c->tw0;
     const unsigned grid = (unsigned)((size_t)P.n * 2 * P.L);
     const int T = P.N / 16;
-    const size_t sm = (size_t)TFHE_BR_NBUF * TFHE_BR_EXW * (P.N / 2) * 16;
+    const size_t sm = (size_t)br_nbuf(c->logN) * TFHE_BR_EXW * (P.N / 2) * 16;
     switch (c->logN) {
       case 9: keygen_bsk_kernel<9><<<grid, T, sm, s>>>(a); break;
       case 10: keygen_bsk_kernel<10><<<grid, T, sm, s>>>(a); break;
@@ -1048,7 +1048,7 @@ static int poly_call(tfhe_ctx* c, int mode, int64_t count, const void* in0, size
   PolyArgs a{};
   a.in0 = c->h2d_a.p; a.in1 = c->h2d_b.p; a.out = c->d2h_out.p; a.tw_tab = c->d_tw; a.mode = mode; a.tw0 = c->tw0;
   const int N = c->P.N, T = N / 16;
-  const size_t sm = (size_t)TFHE_BR_NBUF * TFHE_BR_EXW * (N / 2) * 16;
+  const size_t sm = (size_t)br_nbuf(c->logN) * TFHE_BR_EXW * (N / 2) * 16;
   switch (c->logN) {
     case 9: poly_kernel<9><<<(unsigned)count, T, sm, c->stream>>>(a); break;
     case 10: poly_kernel<10><<<(unsigned)count, T, sm, c->stream>>>(a); break;
