@@ -275,6 +275,20 @@ def main():
     if not np.array_equal(T.tlwe.DecryptBool(got, sk), 1 - (A & B)):
         raise SystemExit("rank %d: e2e outputs are wrong" % rank)
 
+    # --- single-gate latency (BASELINE configs[0] shape: one NAND per call through the C ABI), rank 0 only, untimed part ----
+    single_ms = None
+    if rank == 0:
+        a1, b1, o1 = a_h[0:1].clone(), b_h[0:1].clone(), torch.empty((1, n1), dtype=torch.int32)
+        call = lambda: ctx.lib.tfhe_gate_batch(ctx.h, 1, opv.ctypes.data, 1, a1.data_ptr(), b1.data_ptr(), None, o1.data_ptr())
+        for _ in range(3):
+            call()
+        t1 = time.perf_counter()
+        for _ in range(10):
+            call()
+        single_ms = (time.perf_counter() - t1) / 10 * 1e3
+        if int(T.tlwe.DecryptBool(o1.numpy().view(np.uint32).reshape(1, -1), sk)[0]) != int(1 - (A[0] & B[0])):
+            raise SystemExit("single-gate output is wrong")
+
     # --- reduce over ranks: max time --------------------------------------------------------------------------
     times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -311,6 +325,7 @@ def main():
                          "note": "frac > 1 is possible: co-resident gates share bootstrapping-key rows out of L2"},
             "roofline_fp64": {"algorithmic_tflops": flops / (br_ms * 1e-3) / 1e12, "flops_per_bootstrap": P.flops_per_bootstrap},
             "stage_ms": {"blind_rotate": br_ms, "key_switch": ks_ms, "share_blind_rotate": br_ms / (br_ms + ks_ms)},
+            "single_gate_ms": single_ms,  # one NAND per C-ABI call with host buffers (latency kernel), same key and parameters
             "wall_s_timed_region": t_wall,
         }
         if not args.no_cpu_baseline and world == 1:
