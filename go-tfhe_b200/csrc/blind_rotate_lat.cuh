@@ -160,6 +160,152 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Order-preserving two-group kernel for the parameter sets whose f64 sums are NOT exact (L <= 2: Uint1-5, the programmable
+// bootstraps): the two groups still transform the two polynomials concurrently, but the multiply-accumulate chain keeps
+// the reference's row order — group 0 accumulates rows 0..L-1 from zero, hands BOTH partial spectra to group 1, which
+// (having kept its L digit spectra in registers) continues the very same FMA chain with rows L..2L-1 and returns the A
+// spectrum; then each group inverse-transforms one output.  Every floating-point operation and its operands equal the
+// default kernel's, so the result is bit-identical for every parameter set (variant "latp").
+// Per step: max(L forward + L MAC, L forward) + L MAC + 1 inverse instead of 2L forward + 2L MAC + 2 inverse.
+// ---------------------------------------------------------------------------------------------------------------
+template <int LOGN, int L>
+constexpr size_t br_latp_smem_bytes(int n) {
+  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)2 * 2 * (1 << (LOGN - 1)) * 16 /*exchange: 2 groups x 2 buffers*/ +
+         (size_t)3 * (1 << (LOGN - 1)) * 16 /*partial A, partial B, final A crossing between the groups*/ +
+         (size_t)2 * L * 2 * (1 << (LOGN - 1)) * 16 /*staged key rows: 2 groups x L digits x (A,B)*/ +
+         (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
+}
+
+template <int LOGN, int L, int BGBIT, bool SMALL>
+__global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_latp_kernel(const BrArgs A) {
+  static_assert(L <= 2, "group 1 keeps its L digit spectra in registers");
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                                // [2][N]
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);                           // [2 groups][2][M]
+  double2* cross = reinterpret_cast<double2*>(smem_raw + 8 * N + 64 * M);               // [3][M]: partial A, partial B, final A
+  double2* stage = reinterpret_cast<double2*>(smem_raw + 8 * N + 64 * M + 48 * M);      // [2 groups][L][16][T]
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 64 * M + 48 * M + (size_t)L * 64 * M);
+  const int grp = threadIdx.x / T, tau = threadIdx.x % T;
+  const long long g = blockIdx.x;
+  const int n = A.n;
+  const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+  double2* my_stage = stage + (size_t)grp * L * 16 * T + tau;
+
+  for (int i = threadIdx.x; i < n; i += 2 * T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
+  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
+  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
+  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+  for (int j = threadIdx.x; j < N; j += 2 * T) {
+    const int idx = (j - btil) & (2 * N - 1);
+    const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
+    acc[j] = (idx & N) ? ~va : va;
+    acc[N + j] = (idx & N) ? ~vb : vb;
+  }
+  Fft<LOGN - 1, false, true> fft;
+  fft.init(ex + (size_t)grp * 2 * M, A.tw_tab, tau);
+  fft.bar_id = 1 + grp;
+  __syncthreads();
+
+  const size_t row_stride = (size_t)2 * L * 2 * M;
+  uint32_t* P = acc + grp * N;
+  auto mac = [&](const double2 (&x)[8], int lvl, double2 (&accA)[8], double2 (&accB)[8]) {
+    const double2* ks = my_stage + (size_t)lvl * 16 * T;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const double2 ka = ks[e * T], kb = ks[(8 + e) * T];
+      accA[e].x = fma(x[e].x, ka.x, accA[e].x);
+      accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
+      accA[e].y = fma(x[e].x, ka.y, accA[e].y);
+      accA[e].y = fma(x[e].y, ka.x, accA[e].y);
+      accB[e].x = fma(x[e].x, kb.x, accB[e].x);
+      accB[e].x = fma(-x[e].y, kb.y, accB[e].x);
+      accB[e].y = fma(x[e].x, kb.y, accB[e].y);
+      accB[e].y = fma(x[e].y, kb.x, accB[e].y);
+    }
+  };
+  for (int i = 0; i < n; i++) {
+    const int at = abar[i];
+    if (at == 0) continue;  // uniform over the block
+    {  // this group's L x 16 key values of this step, asynchronously into thread-private slots (hidden behind the transforms)
+      const double2* __restrict__ rows = A.bsk + row_stride * i + (size_t)(grp * L * 2) * M + tau;
+#pragma unroll
+      for (int l = 0; l < L; l++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (size_t)(l * 16 + e) * T)),
+                       "l"(rows + (size_t)(l * 2) * M + e * T) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (size_t)(l * 16 + 8 + e) * T)),
+                       "l"(rows + (size_t)(l * 2 + 1) * M + e * T) : "memory");
+        }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    uint32_t dre[8], dim[8];
+    const int ib = (tau - at) & (2 * N - 1);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      dre[a] = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
+      dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
+    }
+    double2 xs[L][8];
+    double2 accA[8], accB[8];
+#pragma unroll
+    for (int lvl = 0; lvl < L; lvl++) {
+      const int sh = 32 - (lvl + 1) * BGBIT;
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        xs[lvl][a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
+        xs[lvl][a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+      }
+      fft.forward(xs[lvl], A.tw0);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    double2 y[8];
+    if (grp == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
+#pragma unroll
+      for (int lvl = 0; lvl < L; lvl++) mac(xs[lvl], lvl, accA, accB);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { cross[e * T + tau] = accA[e]; cross[M + e * T + tau] = accB[e]; }
+      __syncthreads();  // #1: partials of rows 0..L-1 are out
+      __syncthreads();  // #2: group 1 has finished the chain
+#pragma unroll
+      for (int e = 0; e < 8; e++) y[e] = cross[2 * M + e * T + tau];
+    } else {
+      __syncthreads();  // #1
+#pragma unroll
+      for (int e = 0; e < 8; e++) { accA[e] = cross[e * T + tau]; accB[e] = cross[M + e * T + tau]; }
+#pragma unroll
+      for (int lvl = 0; lvl < L; lvl++) mac(xs[lvl], lvl, accA, accB);
+#pragma unroll
+      for (int e = 0; e < 8; e++) { cross[2 * M + e * T + tau] = accA[e]; y[e] = accB[e]; }
+      __syncthreads();  // #2
+    }
+    fft.inverse(y, A.tw0);
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      const int j = tau + T * a;
+      P[j] += to_torus<SMALL>(y[a].x);
+      P[j + M] += to_torus<SMALL>(y[a].y);
+    }
+    __syncthreads();  // both polynomials updated, `cross` and the stage free
+  }
+
+  if (A.out_mode == 0) {
+    uint32_t* o = A.out + g * (2 * N);
+    for (int j = threadIdx.x; j < 2 * N; j += 2 * T) o[j] = acc[j];
+  } else {
+    uint32_t* o = A.out + g * (N + 1);
+    for (int j = threadIdx.x; j < N; j += 2 * T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
+    if (threadIdx.x == 0) o[N] = acc[N];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // One group of N/16 threads per DIGIT (2L groups, 384 threads at L = 3): all 2L forward transforms of a CMUX step run
 // concurrently, every group writes its two partial products (digit spectrum x key row, for the A and the B output) to
 // shared memory, and the first group of each polynomial sums the 2L partials of "its" output in the reference's row order,

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(512) key_switch_kernel(const uint32_t* __restr
                                                          const uint32_t* __restrict__ ksk,
                                                          uint32_t* __restrict__ out, int N, int n, int basebit,
                                                          int t, int stride, const GateDesc* __restrict__ out_gates,
-                                                         long long instances) {
+                                                         long long instances, int splits) {
   extern __shared__ uint32_t rows[];  // compacted list of non-zero row indices, capacity N*t
   __shared__ int nrows;
   const long long g = blockIdx.x;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(512) key_switch_kernel(const uint32_t* __restr
   // so co-resident ciphertexts (each row is wanted by count/base of them) meet in L2 instead of each streaming its
   // rows from HBM.  Small bases: compact away the k = 0 rows (1/4 of them at base 4); order is irrelevant there
   // because the whole key is L2-resident.
-  const bool ordered = basebit >= 4;
+  const bool ordered = basebit >= 4 || splits > 1;  // a split list must be the same in every block of the ciphertext
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
     const uint32_t abar = src[i] + prec;
     for (int j = 0; j < t; j++) {
@@ -154,11 +154,14 @@ __global__ void __launch_bounds__(512) key_switch_kernel(const uint32_t* __restr
     }
   }
   __syncthreads();
-  const int cnt = ordered ? N * t : nrows;
+  const int cnt_all = ordered ? N * t : nrows;
+  // small batches: blockIdx.y splits the row list of one ciphertext over several blocks (a lone block would stream its
+  // 20-26 MB of key rows through one SM); the slices are combined by atomic adds into a zero-initialised output row
+  const int r_lo = (int)(((long long)cnt_all * blockIdx.y) / splits), cnt = (int)(((long long)cnt_all * (blockIdx.y + 1)) / splits);
   const int ncol4 = stride / 4;
   for (int c4 = threadIdx.x; c4 < ncol4; c4 += blockDim.x) {
     uint4 acc = make_uint4(0u, 0u, 0u, 0u);
-    int r = 0;
+    int r = r_lo;
     for (; r + 8 <= cnt; r += 8) {
       uint4 v[8];
 #pragma unroll
@@ -175,12 +178,26 @@ __global__ void __launch_bounds__(512) key_switch_kernel(const uint32_t* __restr
     const size_t orow = out_gates ? (size_t)out_gates[g / instances].out * instances + (size_t)(g % instances) : (size_t)g;
     uint32_t* o = out + orow * (n + 1);
     const int c = c4 * 4;
-    const uint32_t bterm = src[N];
-    if (c + 0 <= n) o[c + 0] = (c + 0 == n ? bterm : 0u) - acc.x;
-    if (c + 1 <= n) o[c + 1] = (c + 1 == n ? bterm : 0u) - acc.y;
-    if (c + 2 <= n) o[c + 2] = (c + 2 == n ? bterm : 0u) - acc.z;
-    if (c + 3 <= n) o[c + 3] = (c + 3 == n ? bterm : 0u) - acc.w;
+    const uint32_t bterm = (blockIdx.y == 0) ? src[N] : 0u;
+    if (splits == 1) {
+      if (c + 0 <= n) o[c + 0] = (c + 0 == n ? bterm : 0u) - acc.x;
+      if (c + 1 <= n) o[c + 1] = (c + 1 == n ? bterm : 0u) - acc.y;
+      if (c + 2 <= n) o[c + 2] = (c + 2 == n ? bterm : 0u) - acc.z;
+      if (c + 3 <= n) o[c + 3] = (c + 3 == n ? bterm : 0u) - acc.w;
+    } else {
+      if (c + 0 <= n) atomicAdd(o + c + 0, (c + 0 == n ? bterm : 0u) - acc.x);
+      if (c + 1 <= n) atomicAdd(o + c + 1, (c + 1 == n ? bterm : 0u) - acc.y);
+      if (c + 2 <= n) atomicAdd(o + c + 2, (c + 2 == n ? bterm : 0u) - acc.z);
+      if (c + 3 <= n) atomicAdd(o + c + 3, (c + 3 == n ? bterm : 0u) - acc.w);
+    }
   }
+}
+
+// zero the output rows of a split key switch (job -> wire mapping as in key_switch_kernel)
+__global__ void zero_out_rows_kernel(uint32_t* __restrict__ out, int n, const GateDesc* __restrict__ out_gates, long long instances) {
+  const long long g = blockIdx.x;
+  const size_t orow = out_gates ? (size_t)out_gates[g / instances].out * instances + (size_t)(g % instances) : (size_t)g;
+  for (int w = threadIdx.x; w <= n; w += blockDim.x) out[orow * (n + 1) + w] = 0u;
 }
 
 // ksk [rows][n+1] -> [rows][stride], zero padded

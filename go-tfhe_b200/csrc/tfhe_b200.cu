@@ -166,7 +166,15 @@ struct Variant {
   size_t (*br_lat_smem)(int n);
   void (*br_lat2)(const BrArgs);     // latency mode, one group per digit (2L x N/16 threads): <= 1 gate per SM
   size_t (*br_lat2_smem)(int n);
+  void (*br_latp)(const BrArgs);     // latency mode that keeps the reference's accumulation order (L <= 2: the Uint / PBS sets)
+  size_t (*br_latp_smem)(int n);
 };
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto latp_kernel() -> void (*)(const BrArgs) {
+  if constexpr (L <= 2) return blind_rotate_latp_kernel<LOGN, L, BG, SMALL>;
+  else return nullptr;
+}
+template <int LOGN, int L> size_t br_latp_smem(int n) { return br_latp_smem_bytes<LOGN, (L <= 2 ? L : 1)>(n); }
 template <int LOGN, int L, int BG, bool SMALL>
 constexpr auto lat2_kernel() -> void (*)(const BrArgs) {
   if constexpr (LOGN == 10 && SMALL) return blind_rotate_lat2_kernel<LOGN, L, BG, SMALL>;
@@ -239,7 +247,7 @@ constexpr auto tm_kernel() -> void (*)(const BrArgs) {
     br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>(),           \
     tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>(), tms_kernel<LOGN, L, BG, SMALL>(), br_tms_smem<LOGN>,  \
     mg_kernel<LOGN, L, BG, SMALL>(), br_mg_smem<LOGN>, lat_kernel<LOGN, L, BG, SMALL>(), br_lat_smem<LOGN>,  \
-    lat2_kernel<LOGN, L, BG, SMALL>(), br_lat2_smem<LOGN, L> }
+    lat2_kernel<LOGN, L, BG, SMALL>(), br_lat2_smem<LOGN, L>, latp_kernel<LOGN, L, BG, SMALL>(), br_latp_smem<LOGN, L> }
 #ifndef TFHE_BR_MINB_N1024
 #define TFHE_BR_MINB_N1024 4
 #endif
@@ -290,6 +298,9 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   if (c->br_variant == 6 && V.br_txs) V.br_txs<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 5 && V.br_tx) V.br_tx<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   // latency mode with one 64-thread group per digit (2L groups): explicit choice only
+  // order-preserving latency mode (Uint / PBS sets): a batch of at most one ciphertext per SM
+  else if (V.br_latp && (c->br_variant == 12 || (c->br_variant == 0 && c->br_auto_lat && count <= (int64_t)c->sm_count)))
+    V.br_latp<<<(unsigned)count, 2 * T, V.br_latp_smem(c->P.n), s>>>(a);
   else if (V.br_lat2 && c->br_variant == 11)  // measured: not faster than the two-group kernel below, so never picked automatically
     V.br_lat2<<<(unsigned)count, 2 * c->P.L * T, V.br_lat2_smem(c->P.n), s>>>(a);
   // latency mode: a batch that cannot fill the SMs with the throughput kernel (<= 2 gates per SM) gets four warps per gate
@@ -389,8 +400,14 @@ int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32
   // one thread per 16-byte column of a key row, so that the row loop runs once (n = 1071: 268 columns -> 288 threads,
   // not 256 + a second pass with 12 live threads)
   const int ks_threads = std::min(512, std::max(128, (c->ksk_stride / 4 + 31) / 32 * 32));
-  key_switch_kernel<<<(unsigned)count, ks_threads, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
-                                                     c->P.iks_t, c->ksk_stride, out_gates, instances);
+  // fewer ciphertexts than ~2 blocks per SM: split each ciphertext's rows over several blocks
+  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, (2 * (int64_t)c->sm_count) / count));
+  if (splits > 1) {
+    zero_out_rows_kernel<<<(unsigned)count, 128, 0, s>>>(d_out, c->P.n, out_gates, instances);
+    c->launches++;
+  }
+  key_switch_kernel<<<dim3((unsigned)count, (unsigned)splits), ks_threads, sm, s>>>(d_lwe1, c->d_ksk, d_out, c->P.N, c->P.n, c->P.basebit,
+                                                                               c->P.iks_t, c->ksk_stride, out_gates, instances, splits);
   c->launches++;
   CK(c, cudaGetLastError());
   return 0;
@@ -480,6 +497,8 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
   const Variant& V = kVariants[v];
+  if (V.br_latp && (e = cudaFuncSetAttribute(V.br_latp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_latp_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_latp)", e);
   if (V.br_lat2 && (e = cudaFuncSetAttribute(V.br_lat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat2_smem(2048))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_lat2)", e);
   if (V.br_lat && (e = cudaFuncSetAttribute(V.br_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat_smem(4096))) != cudaSuccess)
@@ -523,7 +542,7 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
   if (const char* sel = getenv("TFHE_B200_BR"))
-    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat") ? 9 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat") ? 9 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "latp") ? 12 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
   if (c->br_variant == 10) { c->br_variant = 0; c->br_auto_lat = false; }
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
@@ -1085,6 +1104,10 @@ int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;
   if (variant == 10) { c->br_variant = 0; c->br_auto_lat = false; return TFHE_OK; }  // throughput kernel at every batch size
+  if (variant == 12) {
+    if (!kVariants[c->variant].br_latp) return fail(c, TFHE_ERR_ARG, "the order-preserving latency kernel exists for L <= 2 only");
+    c->br_variant = 12; c->br_auto_lat = true; return TFHE_OK;
+  }
   if (variant == 11) {
     if (!kVariants[c->variant].br_lat2 || c->P.n > 2048) return fail(c, TFHE_ERR_ARG, "the per-digit latency kernel exists for the exact N = 1024 sets only");
     c->br_variant = 11; c->br_auto_lat = true; return TFHE_OK;
