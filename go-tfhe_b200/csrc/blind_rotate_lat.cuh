@@ -271,19 +271,20 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_latp_ke
       for (int lvl = 0; lvl < L; lvl++) mac(xs[lvl], lvl, accA, accB);
 #pragma unroll
       for (int e = 0; e < 8; e++) { cross[e * T + tau] = accA[e]; cross[M + e * T + tau] = accB[e]; }
-      __syncthreads();  // #1: partials of rows 0..L-1 are out
-      __syncthreads();  // #2: group 1 has finished the chain
-#pragma unroll
-      for (int e = 0; e < 8; e++) y[e] = cross[2 * M + e * T + tau];
-    } else {
-      __syncthreads();  // #1
+    }
+    __syncthreads();  // #1: partials of rows 0..L-1 are out
+    if (grp == 1) {
 #pragma unroll
       for (int e = 0; e < 8; e++) { accA[e] = cross[e * T + tau]; accB[e] = cross[M + e * T + tau]; }
 #pragma unroll
       for (int lvl = 0; lvl < L; lvl++) mac(xs[lvl], lvl, accA, accB);
 #pragma unroll
       for (int e = 0; e < 8; e++) { cross[2 * M + e * T + tau] = accA[e]; y[e] = accB[e]; }
-      __syncthreads();  // #2
+    }
+    __syncthreads();  // #2: group 1 has finished the chain
+    if (grp == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; e++) y[e] = cross[2 * M + e * T + tau];
     }
     fft.inverse(y, A.tw0);
 #pragma unroll
