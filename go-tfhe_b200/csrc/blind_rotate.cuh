@@ -52,6 +52,9 @@
 #ifndef TFHE_BR_PF_LATE
 #define TFHE_BR_PF_LATE 0       // 1: the prefetch of the next step's first rows is issued between the two inverse transforms
 #endif
+#ifndef TFHE_BR_CPASYNC
+#define TFHE_BR_CPASYNC 0       // 1: key rows of the next digit staged with cp.async into thread-private shared-memory slots (experiment)
+#endif
 #ifndef TFHE_BR_I2F
 #define TFHE_BR_I2F 0           // 1: signed digits by shift pair + I2F (conversion pipe) instead of mask + exponent-trick DADD; measured 1.4 % slower
 #endif
@@ -507,6 +510,11 @@ struct KeyLdg {
     return __ldg(p + idx);
   }
 };
+struct KeyStage {  // LDG policy + a thread-private shared-memory stage filled one digit ahead by cp.async
+  const double2* __restrict__ p;
+  double2* st;  // this thread's slot 0; slot e of the A row at st[e * T], of the B row at st[(8 + e) * T]
+  __device__ __forceinline__ double2 operator()(int idx) const { return __ldg(p + idx); }
+};
 struct KeyTex {
   cudaTextureObject_t tex;
   int base;  // in double2 units
@@ -545,10 +553,21 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
       }
     }
 #endif
+    if constexpr (std::is_same<Key, KeyStage>::value) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+      for (int e = 0; e < 8; e++) { kA[e] = bk.st[e * T]; kB[e] = bk.st[(8 + e) * T]; }
+#pragma unroll
+      for (int e = 0; e < 8; e++) {  // digit r + 1 (contiguous into the next step's row-set)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + e * T)), "l"(bk.p + rowA + 2 * M + e * T) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + (8 + e) * T)), "l"(bk.p + rowB + 2 * M + e * T) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
       double2 ka, kb;
-      if constexpr (KP) { ka = kA[e]; kb = kB[e]; }
+      if constexpr (KP || std::is_same<Key, KeyStage>::value) { ka = kA[e]; kb = kB[e]; }
       else { ka = bk(rowA + e * T); kb = bk(rowB + e * T); }
       accA[e].x = fma(x[e].x, ka.x, accA[e].x);
       accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
@@ -652,6 +671,7 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
 template <int LOGN>
 constexpr size_t br_smem_bytes(int n) {
   return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)br_nbuf(LOGN) * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [NBUF][EXW][M]*/ +
+         (size_t)(TFHE_BR_CPASYNC ? 2 * (1 << (LOGN - 1)) * 16 : 0) /*thread-private key stage*/ +
          (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
 }
 
@@ -671,7 +691,8 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][EXW][M]
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M);
+  double2* kstage = reinterpret_cast<double2*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M);  // [16][T] if TFHE_BR_CPASYNC
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M + (TFHE_BR_CPASYNC ? 32 * M : 0));
   const int tau = threadIdx.x;
   const long long g = blockIdx.x;
   const int n = A.n;
@@ -702,7 +723,20 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
     if (at == 0) continue;  // X^0: ct1 - ct0 = 0, digits are all zero, the step is an exact no-op
     if constexpr (TEX)
       cmux_rotate_step<LOGN, L, BGBIT, SMALL, false>(acc, fft, KeyTex{A.bsk_tex, (int)(row_stride * i)}, at, A.offset, A.tw0, kA, kB);
-    else if constexpr (TFHE_BR_KPIPE) {
+    else if constexpr (TFHE_BR_CPASYNC) {
+      const KeyStage bk{A.bsk + row_stride * i, kstage + tau};
+      if (pref != i) {  // first step, or the one after a skipped step: (re)stage the first digit
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + e * T)), "l"(bk.p + tau + e * T) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + (8 + e) * T)), "l"(bk.p + M + tau + e * T) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      cmux_rotate_step<LOGN, L, BGBIT, SMALL, false>(acc, fft, bk, at, A.offset, A.tw0, kA, kB);
+      pref = i + 1;
+    } else if constexpr (TFHE_BR_KPIPE) {
       const KeyLdg bk{A.bsk + row_stride * i};
       if (pref != i) {  // first step, or the one after a skipped step
 #pragma unroll
