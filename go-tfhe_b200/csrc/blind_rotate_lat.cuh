@@ -13,6 +13,8 @@
 // enabled: the parameter sets whose rounded result is the exact integer result (SMALL: 80/110/128-bit; DESIGN.md
 // section 2) — outputs are bit-identical to the default kernel and the oracle there.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "blind_rotate.cuh"
 
 namespace tfhe {
@@ -434,6 +436,147 @@ __global__ void __launch_bounds__(2 * L * (1 << (LOGN - 4)), 1) blind_rotate_lat
     for (int j = threadIdx.x; j < N; j += NG * T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
     if (threadIdx.x == 0) o[N] = acc[N];
   }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One gate on a CLUSTER of 2L thread blocks (2L SMs), one block of N/16 threads per digit (variant "cl").
+// The per-digit kernel above shares one SM's FP64 pipe and key bandwidth among its 2L transforms; here every digit has
+// an SM of its own and the blocks talk through distributed shared memory (cooperative_groups::this_cluster):
+//   block r:            digit r of polynomial r / L (from a local copy of that polynomial) -> forward transform ->
+//                       partial products with key row r for both outputs, left in LOCAL shared memory; the key rows of
+//                       the next step are staged by cp.async meanwhile
+//   cluster barrier
+//   blocks 0 and L:     read the 2L partials of output A resp. B out of the other blocks' shared memory, sum them in row
+//                       order, inverse-transform, round, and write the updated polynomial into the local copies of the L
+//                       blocks that decompose it
+//   cluster barrier
+// One forward + one inverse transform, two cluster barriers and ~100 KiB of DSMEM traffic per step.  For batches of at
+// most (SMs / 2L) gates — the single gates.NAND call; exact parameter sets only (partial sums, not the FMA chain).
+// ---------------------------------------------------------------------------------------------------------------
+template <int LOGN>
+constexpr size_t br_cl_smem_bytes(int n) {
+  return (size_t)4 * (1 << LOGN) /*one polynomial of the accumulator*/ + (size_t)2 * (1 << (LOGN - 1)) * 16 /*exchange*/ +
+         (size_t)2 * (1 << (LOGN - 1)) * 16 /*partial products for A and B*/ + (size_t)2 * (1 << (LOGN - 1)) * 16 /*key stage*/ +
+         (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
+}
+
+template <int LOGN, int L, int BGBIT, bool SMALL>
+__global__ void __cluster_dims__(2 * L, 1, 1) __launch_bounds__((1 << (LOGN - 4)), 1) blind_rotate_cl_kernel(const BrArgs A) {
+  static_assert(SMALL, "partial sums are reordered: exact parameter sets only");
+  namespace cg = cooperative_groups;
+  constexpr int N = 1 << LOGN, M = N / 2, T = M / 8, NG = 2 * L;
+  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint32_t* P = reinterpret_cast<uint32_t*>(smem_raw);                                   // [N]: polynomial rank / L
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 4 * N);                            // [2][M]
+  double2* part = reinterpret_cast<double2*>(smem_raw + 4 * N + 32 * M);                 // [2 outputs][M]
+  double2* stage = reinterpret_cast<double2*>(smem_raw + 4 * N + 64 * M);                // [16][T]
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 4 * N + 96 * M);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int poly = rank / L, lvl = rank % L;
+  const int tau = threadIdx.x;
+  const long long g = blockIdx.x / NG;
+  const int n = A.n;
+  const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+
+  for (int i = tau; i < n; i += T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
+  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
+  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
+  const uint32_t* __restrict__ tv = (A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec) + poly * N;
+  for (int j = tau; j < N; j += T) {
+    const int idx = (j - btil) & (2 * N - 1);
+    const uint32_t v = tv[idx & (N - 1)];
+    P[j] = (idx & N) ? ~v : v;
+  }
+  Fft<LOGN - 1, false, false> fft;
+  fft.init(ex, A.tw_tab, tau);
+  double2* my_stage = stage + tau;
+  const size_t row_stride = (size_t)2 * L * 2 * M;
+  auto stage_keys = [&](int i) {
+    const double2* __restrict__ rowA = A.bsk + row_stride * i + (size_t)(rank * 2) * M + tau;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + e * T)), "l"(rowA + e * T) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (8 + e) * T)), "l"(rowA + M + e * T) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // remote views: the partial buffers of every block (for the two summing blocks) and the polynomial copies this block feeds
+  double2* rpart[NG];
+#pragma unroll
+  for (int r = 0; r < NG; r++) rpart[r] = cluster.map_shared_rank(part, r);
+  uint32_t* rP[L];
+#pragma unroll
+  for (int l = 0; l < L; l++) rP[l] = cluster.map_shared_rank(P, poly * L + l);
+  __syncthreads();
+  auto next_step = [&](int i) { while (i < n && abar[i] == 0) i++; return i; };  // X^0 steps are exact no-ops
+  int i = next_step(0);
+  if (i < n) stage_keys(i);
+  cluster.sync();
+  const int sh = 32 - (lvl + 1) * BGBIT;
+  while (i < n) {
+    const int at = abar[i];
+    double2 x[8];
+    {
+      const int ib = (tau - at) & (2 * N - 1);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        const uint32_t wre = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
+        const uint32_t wim = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
+        x[a].x = field_to_double((wre >> sh) & MASK, BIAS);
+        x[a].y = field_to_double((wim >> sh) & MASK, BIAS);
+      }
+    }
+    fft.forward(x, A.tw0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const double2 ka = my_stage[e * T], kb = my_stage[(8 + e) * T];
+      part[e * T + tau] = make_double2(fma(x[e].x, ka.x, -(x[e].y * ka.y)), fma(x[e].x, ka.y, x[e].y * ka.x));
+      part[M + e * T + tau] = make_double2(fma(x[e].x, kb.x, -(x[e].y * kb.y)), fma(x[e].x, kb.y, x[e].y * kb.x));
+    }
+    const int inext = next_step(i + 1);
+    if (inext < n) stage_keys(inext);  // hidden behind the barriers and the inverse transform
+    cluster.sync();                    // every block's partial products are in its shared memory
+    if (lvl == 0) {                    // blocks 0 and L: output `poly` = sum over all 2L digits, in row order
+      double2 y[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) y[e] = rpart[0][(size_t)poly * M + e * T + tau];
+#pragma unroll
+      for (int r = 1; r < NG; r++) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const double2 o = rpart[r][(size_t)poly * M + e * T + tau];
+          y[e].x += o.x;
+          y[e].y += o.y;
+        }
+      }
+      fft.inverse(y, A.tw0);
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        const uint32_t v0 = P[j] + to_torus<SMALL>(y[a].x), v1 = P[j + M] + to_torus<SMALL>(y[a].y);
+#pragma unroll
+        for (int l = 0; l < L; l++) { rP[l][j] = v0; rP[l][j + M] = v1; }  // l = 0 is this block's own copy
+      }
+    }
+    cluster.sync();  // updated polynomials visible everywhere; partial buffers free
+    i = inext;
+  }
+  if (lvl == 0) {
+    if (A.out_mode == 0) {
+      uint32_t* o = A.out + g * (2 * N) + poly * N;
+      for (int j = tau; j < N; j += T) o[j] = P[j];
+    } else {  // sample extract at 0: block 0 holds polynomial A, block L holds B[0]
+      uint32_t* o = A.out + g * (N + 1);
+      if (poly == 0) { for (int j = tau; j < N; j += T) o[j] = (j == 0) ? P[0] : ~P[N - j]; }
+      else if (tau == 0) o[N] = P[0];
+    }
+  }
+  cluster.sync();  // no block may exit while others can still address its shared memory
 }
 
 }  // namespace tfhe

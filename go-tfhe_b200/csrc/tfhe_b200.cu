@@ -83,6 +83,7 @@ struct tfhe_ctx {
   // how blind rotate reads the key rows: 0 = LDG straight from L2 (default, fastest measured), 1 = TMA-staged through
   // shared memory (cp.async.bulk + mbarrier), 2 = texture fetches.  See profiles/ for the measurements behind the default.
   int br_variant = 0;
+  bool br_auto_cl = false;   // variant 0 may also pick the cluster kernel for a handful of gates (set once measured)
   bool br_auto_lat = true;   // variant 0 picks the latency kernel for batches of <= 2 gates per SM (exact parameter sets)
   cudaTextureObject_t bsk_tex = 0;
   // warp-per-gate kernel (N = 1024 only): its own key layout and twiddle tables
@@ -168,7 +169,15 @@ struct Variant {
   size_t (*br_lat2_smem)(int n);
   void (*br_latp)(const BrArgs);     // latency mode that keeps the reference's accumulation order (L <= 2: the Uint / PBS sets)
   size_t (*br_latp_smem)(int n);
+  void (*br_cl)(const BrArgs);       // one gate on a cluster of 2L blocks (one SM per digit, DSMEM): a handful of gates
+  size_t (*br_cl_smem)(int n);
 };
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto cl_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10 && SMALL && 2 * L <= 8) return blind_rotate_cl_kernel<LOGN, L, BG, SMALL>;
+  else return nullptr;
+}
+template <int LOGN> size_t br_cl_smem(int n) { return br_cl_smem_bytes<LOGN>(n); }
 template <int LOGN, int L, int BG, bool SMALL>
 constexpr auto latp_kernel() -> void (*)(const BrArgs) {
   if constexpr (L <= 2) return blind_rotate_latp_kernel<LOGN, L, BG, SMALL>;
@@ -247,7 +256,8 @@ constexpr auto tm_kernel() -> void (*)(const BrArgs) {
     br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>(),           \
     tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>(), tms_kernel<LOGN, L, BG, SMALL>(), br_tms_smem<LOGN>,  \
     mg_kernel<LOGN, L, BG, SMALL>(), br_mg_smem<LOGN>, lat_kernel<LOGN, L, BG, SMALL>(), br_lat_smem<LOGN>,  \
-    lat2_kernel<LOGN, L, BG, SMALL>(), br_lat2_smem<LOGN, L>, latp_kernel<LOGN, L, BG, SMALL>(), br_latp_smem<LOGN, L> }
+    lat2_kernel<LOGN, L, BG, SMALL>(), br_lat2_smem<LOGN, L>, latp_kernel<LOGN, L, BG, SMALL>(), br_latp_smem<LOGN, L>,  \
+    cl_kernel<LOGN, L, BG, SMALL>(), br_cl_smem<LOGN> }
 #ifndef TFHE_BR_MINB_N1024
 #define TFHE_BR_MINB_N1024 4
 #endif
@@ -298,6 +308,9 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   if (c->br_variant == 6 && V.br_txs) V.br_txs<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 5 && V.br_tx) V.br_tx<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   // latency mode with one 64-thread group per digit (2L groups): explicit choice only
+  // a handful of gates: one cluster of 2L blocks (2L SMs) per gate
+  else if (V.br_cl && (c->br_variant == 13 || (c->br_variant == 0 && c->br_auto_lat && c->br_auto_cl && count <= (int64_t)c->sm_count / (2 * c->P.L) / 2)))
+    V.br_cl<<<(unsigned)(count * 2 * c->P.L), T, V.br_cl_smem(c->P.n), s>>>(a);
   // order-preserving latency mode (Uint / PBS sets): a batch of at most one ciphertext per SM
   else if (V.br_latp && (c->br_variant == 12 || (c->br_variant == 0 && c->br_auto_lat && count <= (int64_t)c->sm_count)))
     V.br_latp<<<(unsigned)count, 2 * T, V.br_latp_smem(c->P.n), s>>>(a);
@@ -497,6 +510,8 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
   const Variant& V = kVariants[v];
+  if (V.br_cl && (e = cudaFuncSetAttribute(V.br_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_cl_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_cl)", e);
   if (V.br_latp && (e = cudaFuncSetAttribute(V.br_latp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_latp_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_latp)", e);
   if (V.br_lat2 && (e = cudaFuncSetAttribute(V.br_lat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat2_smem(2048))) != cudaSuccess)
@@ -542,7 +557,7 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
   if (const char* sel = getenv("TFHE_B200_BR"))
-    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat") ? 9 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "latp") ? 12 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat") ? 9 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "latp") ? 12 : !strcmp(sel, "cl") ? 13 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
   if (c->br_variant == 10) { c->br_variant = 0; c->br_auto_lat = false; }
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
@@ -1104,6 +1119,10 @@ int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;
   if (variant == 10) { c->br_variant = 0; c->br_auto_lat = false; return TFHE_OK; }  // throughput kernel at every batch size
+  if (variant == 13) {
+    if (!kVariants[c->variant].br_cl) return fail(c, TFHE_ERR_ARG, "the cluster kernel exists for the exact N = 1024 sets only");
+    c->br_variant = 13; c->br_auto_lat = true; return TFHE_OK;
+  }
   if (variant == 12) {
     if (!kVariants[c->variant].br_latp) return fail(c, TFHE_ERR_ARG, "the order-preserving latency kernel exists for L <= 2 only");
     c->br_variant = 12; c->br_auto_lat = true; return TFHE_OK;

@@ -198,7 +198,7 @@ class Context:
 
     def set_blind_rotate_variant(self, variant):
         """'ldg' (default) | 'tma' | 'tex' — how key rows reach the MAC; results are identical."""
-        v = {"ldg": 0, "tma": 1, "tex": 2, "w16": 3, "tmem": 4, "tmex": 5, "tmex+tma": 6, "tms": 7, "mg": 8, "lat": 9, "throughput": 10, "lat2": 11, "latp": 12}[variant] if isinstance(variant, str) else int(variant)
+        v = {"ldg": 0, "tma": 1, "tex": 2, "w16": 3, "tmem": 4, "tmex": 5, "tmex+tma": 6, "tms": 7, "mg": 8, "lat": 9, "throughput": 10, "lat2": 11, "latp": 12, "cl": 13}[variant] if isinstance(variant, str) else int(variant)
         self._ck(self.lib.tfhe_ctx_set_blind_rotate_variant(self.h, v), "tfhe_ctx_set_blind_rotate_variant")
 
     def set_key_switch_variant(self, variant):

@@ -183,7 +183,9 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
  * most two gates per SM), 10 = variant 0 without that switch, 11 = latency mode with one 64-thread group per digit (2L
  * groups; measured no faster than 9, explicit choice only), 12 = latency mode for the L <= 2 sets (Uint1-5 / programmable
  * bootstraps): two groups transform the two polynomials concurrently and pass the accumulation chain on in the reference's
- * row order, bit-identical for every set; variant 0 uses it for at most one ciphertext per SM.  All compute identical results;
+ * row order, bit-identical for every set; variant 0 uses it for at most one ciphertext per SM, 13 = one gate on a thread-block
+ * cluster of 2L blocks (one SM per digit, partial products through distributed shared memory; exact N = 1024 sets;
+ * measured no faster than 9, explicit choice only).  All compute identical results;
  * the default is the fastest measured (profiles/r01_experiments.md). */
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
 /* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default: the contraction wherever it exists), 1 = one block per

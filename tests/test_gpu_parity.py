@@ -87,6 +87,8 @@ def test_key_fetch_variants_agree(O, gpu, name):
             outs["lat"] = ctx.blind_rotate_batch(ct)
             ctx.set_blind_rotate_variant("lat2")  # one 64-thread group per digit
             outs["lat2"] = ctx.blind_rotate_batch(ct)
+            ctx.set_blind_rotate_variant("cl")    # one cluster of 2L blocks per gate, partial products through DSMEM
+            outs["cl"] = ctx.blind_rotate_batch(ct)
             ctx.set_blind_rotate_variant("ldg")  # default: picks a latency kernel by itself for this batch size
             outs["auto"] = ctx.blind_rotate_batch(ct)
         if name != "80":  # order-preserving latency kernel of the L <= 2 sets: bit-identical by construction
@@ -121,7 +123,7 @@ def test_key_fetch_variants_agree(O, gpu, name):
         assert np.array_equal(outs["ldg"], outs["latp"]) and np.array_equal(outs["ldg"], outs["autop"])
     if "lat" in outs:
         assert np.array_equal(outs["ldg"], outs["lat"]) and np.array_equal(outs["ldg"], outs["auto"])
-        assert np.array_equal(outs["ldg"], outs["lat2"])
+        assert np.array_equal(outs["ldg"], outs["lat2"]) and np.array_equal(outs["ldg"], outs["cl"])
     if name == "80":
         ev = O.Evaluator(P.N)
         want = np.stack([ev.blind_rotate(P, c, ck.testvec, ck.bsk_fft, ck.offset) for c in ct])
