@@ -305,6 +305,28 @@ def test_full_size_batch_properties(T, gpu):
     assert np.array_equal(got[0], got[4095])
 
 
+@pytest.mark.parametrize("count", [1, 2, 147, 148, 149, 295, 296, 297, 593])
+def test_kernel_selection_boundaries(T, gpu, count):
+    """The engine picks kernels by batch size (latency kernels up to 2 gates per SM, throughput kernel above; tensor-core key
+    switch everywhere): on both sides of every threshold the default must give the very same words as the throughput
+    kernel + row-gather key switch, and decrypt to the truth table."""
+    P, sk, ck, ctx = gpu("80")
+    rng = np.random.default_rng(count)
+    A = rng.integers(0, 2, count).astype(np.uint8)
+    B = rng.integers(0, 2, count).astype(np.uint8)
+    a, b = sk.encrypt_bool(A, 700 + count), sk.encrypt_bool(B, 900 + count)
+    got = ctx.gate_batch("XOR", a, b)
+    try:
+        ctx.set_blind_rotate_variant("throughput")
+        ctx.set_key_switch_variant("gather")
+        ref = ctx.gate_batch("XOR", a, b)
+    finally:
+        ctx.set_blind_rotate_variant("ldg")
+        ctx.set_key_switch_variant("auto")
+    assert np.array_equal(got, ref)
+    assert np.array_equal(sk.decrypt_bool(got), A ^ B)
+
+
 def test_full_size_adder_circuits_config3(T, O, gpu):
     """BASELINE config 3 size: 8-bit ripple-carry adder x 1024 instances (40 960 bootstraps in 17 dependent levels, every
     level's key switch on the tensor-core path with the job -> wire scatter) — every sum must equal (x + y) mod 256, and
