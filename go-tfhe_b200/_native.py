@@ -22,7 +22,7 @@ ENGINE_SYMBOLS = [
     "tfhe_ctx_create", "tfhe_ctx_destroy", "tfhe_last_error", "tfhe_ctx_load_cloudkey",
     "tfhe_ctx_load_cloudkey_device", "tfhe_bootstrap_batch", "tfhe_gate_batch", "tfhe_blind_rotate_batch",
     "tfhe_cmux_batch", "tfhe_sample_extract_batch", "tfhe_key_switch_batch", "tfhe_bootstrap_batch_device",
-    "tfhe_gate_batch_device", "tfhe_circuit_run", "tfhe_to_fourier_batch", "tfhe_to_poly_batch", "tfhe_mul_poly_batch", "tfhe_ctx_kernel_launches", "tfhe_ctx_set_timing", "tfhe_ctx_set_blind_rotate_variant", "tfhe_ctx_set_key_switch_variant", "tfhe_ctx_generate_cloudkey", "tfhe_ctx_collect_timing", "tfhe_ctx_algorithmic_bytes_per_bootstrap", "tfhe_version",
+    "tfhe_gate_batch_device", "tfhe_circuit_run", "tfhe_to_fourier_batch", "tfhe_to_poly_batch", "tfhe_mul_poly_batch", "tfhe_ctx_kernel_launches", "tfhe_ctx_set_timing", "tfhe_ctx_set_blind_rotate_variant", "tfhe_ctx_set_blind_rotate_chunk_steps", "tfhe_ctx_set_key_switch_variant", "tfhe_ctx_generate_cloudkey", "tfhe_ctx_collect_timing", "tfhe_ctx_algorithmic_bytes_per_bootstrap", "tfhe_version",
 ]
 CLIENT_SYMBOLS = [
     "tfhe_client_secret_key", "tfhe_client_encrypt_bool", "tfhe_client_decrypt_bool", "tfhe_client_encrypt_message",
@@ -63,6 +63,7 @@ def engine():
         lib.tfhe_circuit_run.argtypes = [vp, i64, i32, i32, vp, vp, i32, vp, vp]
         lib.tfhe_ctx_set_timing.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_set_blind_rotate_variant.argtypes = [vp, ctypes.c_int]
+        lib.tfhe_ctx_set_blind_rotate_chunk_steps.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_set_key_switch_variant.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_generate_cloudkey.argtypes = [vp, vp, vp, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp]
         lib.tfhe_ctx_collect_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 4)]

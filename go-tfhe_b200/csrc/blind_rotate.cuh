@@ -43,20 +43,8 @@
 #ifndef TFHE_BR_PAIR_FWD
 #define TFHE_BR_PAIR_FWD 0      // forward transforms of consecutive decomposition levels run interleaved in pairs
 #endif
-#ifndef TFHE_BR_KPIPE
-#define TFHE_BR_KPIPE 0         // 1: key rows are software-pipelined in registers: the 16 loads of digit r+1 are issued right after the MAC of digit r (across the loop back-edge and into the next step)
-#endif
 #ifndef TFHE_BR_PF_L1
 #define TFHE_BR_PF_L1 1         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread)
-#endif
-#ifndef TFHE_BR_PF_LATE
-#define TFHE_BR_PF_LATE 0       // 1: the prefetch of the next step's first rows is issued between the two inverse transforms
-#endif
-#ifndef TFHE_BR_CPASYNC
-#define TFHE_BR_CPASYNC 0       // 1: key rows of the next digit staged with cp.async into thread-private shared-memory slots (experiment)
-#endif
-#ifndef TFHE_BR_I2F
-#define TFHE_BR_I2F 0           // 1: signed digits by shift pair + I2F (conversion pipe) instead of mask + exponent-trick DADD; measured 1.4 % slower
 #endif
 #ifndef TFHE_BR_KO
 #define TFHE_BR_KO 0            // TIMING EXPERIMENTS ONLY (wrong results): bit 0 = no exchanges, bit 1 = no key loads, bit 2 = no barrier in exchanges
@@ -74,6 +62,9 @@
 #endif
 __host__ __device__ constexpr bool br_warp_ex(int logn) { return TFHE_BR_WARP_EX || logn >= TFHE_BR_WARP_EX_LOGN; }
 __host__ __device__ constexpr int br_nbuf(int logn) { return br_warp_ex(logn) ? 3 : 2; }  // exchange buffers per transform group
+#ifndef TFHE_EXPERIMENTAL
+#define TFHE_EXPERIMENTAL 0
+#endif
 #define TFHE_PRAGMA_(x) _Pragma(#x)
 #define TFHE_UNROLL(n) TFHE_PRAGMA_(unroll n)
 
@@ -94,6 +85,13 @@ struct BrArgs {
   uint32_t offset;          // CloudKey.DecompositionOffset
   int out_mode;
   Tw4 tw0;                  // pass-0 twiddles (same for every thread; lives in the constant bank)
+  // work distribution of the persistent throughput kernel (blind_rotate_kernel); ignored by the latency kernels
+  long long count;          // gates in this launch
+  int nchunks;              // work items per gate (1 = a whole gate per item)
+  int chunk_steps;          // CMUX steps per work item, nchunks * chunk_steps >= n
+  uint32_t* scratch;        // [count][2][N] accumulator hand-over between the items of a gate (nchunks > 1)
+  unsigned int* ctl;        // [0] next work item, [1] finished blocks; zero at launch, re-zeroed by the last block
+  int* progress;            // [count] items finished per gate (nchunks > 1); zero at launch, re-zeroed by the last block
 };
 
 struct CmuxArgs {
@@ -479,6 +477,25 @@ __device__ __forceinline__ double field_to_double(uint32_t field, double bias) {
   return __hiloint2double(0x43300000, (int)field) - bias;
 }
 
+// Gadget digit (poly/decomposer.go:55-66) of the level whose field starts at bit `sh` of w = coefficient + offset,
+// returned SCALED by 2^sh: ((w >> sh) & (Bg-1)) - Bg/2, times 2^sh.  The field is masked IN PLACE (no shift) into the
+// low mantissa word of 2^52, so a digit costs one LOP3 + one DADD.  Transforms are linear and powers of two are exact,
+// so the spectrum is the unscaled one times 2^sh; the bootstrapping-key rows of that level are stored scaled by 2^-sh
+// (bsk_repack_kernel) and every product x * k — hence every rounding — is bit-identical to the unscaled computation.
+template <int BGBIT>
+__device__ __forceinline__ double digit_scaled(uint32_t w, int sh) {
+  constexpr uint32_t MASK0 = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
+  const double v = __hiloint2double(0x43300000, (int)(w & (MASK0 << sh)));
+  const double bias = __hiloint2double(0x43300000, (int)(1u << (BGBIT - 1 + sh)));  // 2^52 + (Bg/2) 2^sh
+  return v - bias;
+}
+// scale applied to the key rows that multiply the digits of level lvl (rows lvl and L + lvl of every row-set)
+__host__ __device__ inline double digit_key_scale(int bgbit, int lvl) {
+  double s = 1.0;
+  for (int k = 0; k < 32 - (lvl + 1) * bgbit; k++) s *= 0.5;
+  return s;
+}
+
 // Spectrum-domain result -> torus word.  poly/fourier_transform.go:88-125: round(x - 2^32 round(x / 2^32))
 // then uint32(int64(.)).  SMALL: |y| < 2^51 guaranteed by the parameter set, so one magic-number add
 // yields round-to-nearest(y) mod 2^32 (ties cannot occur where the result is exact).
@@ -510,11 +527,6 @@ struct KeyLdg {
     return __ldg(p + idx);
   }
 };
-struct KeyStage {  // LDG policy + a thread-private shared-memory stage filled one digit ahead by cp.async
-  const double2* __restrict__ p;
-  double2* st;  // this thread's slot 0; slot e of the A row at st[e * T], of the B row at st[(8 + e) * T]
-  __device__ __forceinline__ double2 operator()(int idx) const { return __ldg(p + idx); }
-};
 struct KeyTex {
   cudaTextureObject_t tex;
   int base;  // in double2 units
@@ -524,15 +536,27 @@ struct KeyTex {
   }
 };
 
-// KP = true (LDG policy only): kA/kB hold the rows of the first digit on entry and the first digit of the NEXT row-set
-// (bk + one step) on exit; every MAC is followed at once by the loads of the digit after it.
-template <int LOGN, int L, int BGBIT, bool SMALL, bool KP, class Key>
-__device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, false>& fft, const Key bk,
-                                                 int at, uint32_t offset, const Tw4& tw0, double2 (&kA)[8],
-                                                 double2 (&kB)[8]) {
+// Accumulator TRLWE in shared memory: [2 polynomials][EXT * N] words.  EXT = 1: the N coefficients.  EXT = 2: followed
+// by their complements, so that (X^k P)[j] (buffer_methods.go:133-164: P[idx] or ~P[idx - N], idx = (j - k) mod 2N) is
+// one load at idx.  EXT = 3: followed by the coefficients again, so that idx + offsets < 3N needs no wrap either.
+#ifndef TFHE_BR_ACC_EXT
+#define TFHE_BR_ACC_EXT 1
+#endif
+template <int LOGN>
+struct AccBuf {
+  static constexpr int N = 1 << LOGN, EXT = TFHE_BR_ACC_EXT, STRIDE = EXT * N;
+  __device__ __forceinline__ static void store(uint32_t* P, int j, uint32_t v) {
+    P[j] = v;
+    if constexpr (EXT >= 2) P[N + j] = ~v;
+    if constexpr (EXT >= 3) P[2 * N + j] = v;
+  }
+};
+
+template <int LOGN, int L, int BGBIT, bool SMALL, class Key>
+__device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, false>& fft, const Key bk, int at,
+                                                 uint32_t offset, const Tw4& tw0) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
-  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
-  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
+  using AB = AccBuf<LOGN>;
   const int tau = fft.tau;
   double2 accA[8], accB[8];
 #pragma unroll
@@ -544,31 +568,14 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
     const int rowB = rowA + M;
 #if TFHE_BR_PF_L1
     if constexpr (!std::is_same<Key, KeyTex>::value) {  // rows of digit r + d (contiguous into the next step's row-set)
-      // rows that belong to the NEXT step are requested later (between the two inverse transforms): issued here they
-      // would have to survive both inverse transforms in an L1 that four blocks stream 96 KiB per step through
-      if (!TFHE_BR_PF_LATE || r + TFHE_BR_PF_L1 < 2 * L) {
-        const char* pf = reinterpret_cast<const char*>(bk.p + (r + TFHE_BR_PF_L1) * 2 * M) + tau * 128;
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
-      }
+      const char* pf = reinterpret_cast<const char*>(bk.p + (r + TFHE_BR_PF_L1) * 2 * M) + tau * 128;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
     }
 #endif
-    if constexpr (std::is_same<Key, KeyStage>::value) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-      for (int e = 0; e < 8; e++) { kA[e] = bk.st[e * T]; kB[e] = bk.st[(8 + e) * T]; }
-#pragma unroll
-      for (int e = 0; e < 8; e++) {  // digit r + 1 (contiguous into the next step's row-set)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + e * T)), "l"(bk.p + rowA + 2 * M + e * T) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + (8 + e) * T)), "l"(bk.p + rowB + 2 * M + e * T) : "memory");
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      double2 ka, kb;
-      if constexpr (KP || std::is_same<Key, KeyStage>::value) { ka = kA[e]; kb = kB[e]; }
-      else { ka = bk(rowA + e * T); kb = bk(rowB + e * T); }
+      const double2 ka = bk(rowA + e * T), kb = bk(rowB + e * T);
       accA[e].x = fma(x[e].x, ka.x, accA[e].x);
       accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
       accA[e].y = fma(x[e].x, ka.y, accA[e].y);
@@ -578,105 +585,98 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
       accB[e].y = fma(x[e].x, kb.y, accB[e].y);
       accB[e].y = fma(x[e].y, kb.x, accB[e].y);
     }
-    if constexpr (KP) {  // rows of digit r + 1 (row-sets are contiguous: after the last digit this is the next step)
-#pragma unroll
-      for (int e = 0; e < 8; e++) {
-        kA[e] = bk(rowA + 2 * M + e * T);
-        kB[e] = bk(rowB + 2 * M + e * T);
-      }
-    }
   };
 
   TFHE_UNROLL(TFHE_BR_UNROLL_POLY)
   for (int poly = 0; poly < 2; poly++) {
-    const uint32_t* P = acc + poly * N;
+    const uint32_t* P = acc + poly * AB::STRIDE;
+    // decomposition input w = (X^at * P - P)[j] + offset for this thread's 16 coefficients j = tau + T a' (a' < 16);
+    // rotated index idx = (j - at) mod 2N = ib + T a' walks N consecutive multiples of T: it wraps past N exactly once.
     uint32_t dre[8], dim[8];
     const int ib = (tau - at) & (2 * N - 1);
-    // digit_l = ((tmp >> sh_l) & (Bg-1)) - Bg/2 (decomposer.go:55-66).  Flipping the top bit of every field once
-    // (XOR with sum_l (Bg/2) << sh_l) turns "field - Bg/2" into a plain sign extension of the field, so a digit is two
-    // shifts and an exact int -> double conversion on the conversion pipe; the FP64 pipe and one move per digit are saved.
-    constexpr uint32_t XFLIP = []() { uint32_t v = 0; for (int l = 0; l < L; l++) v |= (1u << (BGBIT - 1)) << (32 - (l + 1) * BGBIT); return v; }();
+    if constexpr (AB::EXT == 3) {
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      const int j = tau + T * a;
-      dre[a] = rot_read<N>(P, ib + T * a) - P[j] + offset;
-      dim[a] = rot_read<N>(P, ib + T * a + M) - P[j + M] + offset;
-      if (TFHE_BR_I2F) { dre[a] ^= XFLIP; dim[a] ^= XFLIP; }
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        dre[a] = P[ib + T * a] - P[j] + offset;
+        dim[a] = P[ib + T * a + M] - P[j + M] + offset;
+      }
+    } else if constexpr (AB::EXT == 2) {
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        dre[a] = P[(ib + T * a) & (2 * N - 1)] - P[j] + offset;
+        dim[a] = P[(ib + T * a + M) & (2 * N - 1)] - P[j + M] + offset;
+      }
+    } else {
+      const int p0 = ib & (N - 1);
+      const uint32_t s0 = 0u - (uint32_t)((ib >> LOGN) & 1);  // complement mask of a' = 0
+      const int wrap = (N - p0 + T - 1) / T;                  // first a' whose index wraps (1..16): the mask flips there
+#pragma unroll
+      for (int a = 0; a < 8; a++) {
+        const int j = tau + T * a;
+        const uint32_t mre = s0 ^ (uint32_t)((wrap - 1 - a) >> 31), mim = s0 ^ (uint32_t)((wrap - 9 - a) >> 31);
+        dre[a] = (P[(p0 + T * a) & (N - 1)] ^ mre) - P[j] + offset;
+        dim[a] = (P[(p0 + T * a + M) & (N - 1)] ^ mim) - P[j + M] + offset;
+      }
     }
-    auto digits = [&](double2 (&x)[8], int lvl) {
+    TFHE_UNROLL(TFHE_BR_UNROLL_LVL)
+    for (int lvl = 0; lvl < L; lvl++) {
+      double2 x[8];
       const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
       for (int a = 0; a < 8; a++) {
-        if (TFHE_BR_I2F) {
-          x[a].x = (double)((int32_t)(dre[a] << (lvl * BGBIT)) >> (32 - BGBIT));
-          x[a].y = (double)((int32_t)(dim[a] << (lvl * BGBIT)) >> (32 - BGBIT));
-        } else {
-          x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-          x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
-        }
+        x[a].x = digit_scaled<BGBIT>(dre[a], sh);
+        x[a].y = digit_scaled<BGBIT>(dim[a], sh);
       }
-    };
-    int lvl = 0;
-#if TFHE_BR_PAIR_FWD
-#pragma unroll
-    for (; lvl + 1 < L; lvl += 2) {
-      double2 x[8], y[8];
-      digits(x, lvl);
-      digits(y, lvl + 1);
-      fft.forward2(x, y, tw0);
-      mac(x, poly * L + lvl);
-      mac(y, poly * L + lvl + 1);
-    }
-#endif
-    TFHE_UNROLL(TFHE_BR_UNROLL_LVL)
-    for (; lvl < L; lvl++) {
-      double2 x[8];
-      digits(x, lvl);
       fft.forward(x, tw0);
       mac(x, poly * L + lvl);
     }
   }
-#if TFHE_BR_PAIR_INV
-  fft.inverse2(accA, accB, tw0);
-#else
   fft.inverse(accA, tw0);
-#endif
 #pragma unroll
   for (int a = 0; a < 8; a++) {
     const int j = tau + T * a;
-    acc[j] += to_torus<SMALL>(accA[a].x);
-    acc[j + M] += to_torus<SMALL>(accA[a].y);
+    AB::store(acc, j, acc[j] + to_torus<SMALL>(accA[a].x));
+    AB::store(acc, j + M, acc[j + M] + to_torus<SMALL>(accA[a].y));
   }
-#if TFHE_BR_PF_L1 && TFHE_BR_PF_LATE
-  if constexpr (!std::is_same<Key, KeyTex>::value) {
-#pragma unroll
-    for (int d = 0; d < TFHE_BR_PF_L1; d++) {
-      const char* pf = reinterpret_cast<const char*>(bk.p + (2 * L + d) * 2 * M) + tau * 128;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + T * 128));
-    }
-  }
-#endif
-#if !TFHE_BR_PAIR_INV
   fft.inverse(accB, tw0);
-#endif
+  uint32_t* PB = acc + AB::STRIDE;
 #pragma unroll
   for (int a = 0; a < 8; a++) {
     const int j = tau + T * a;
-    acc[N + j] += to_torus<SMALL>(accB[a].x);
-    acc[N + j + M] += to_torus<SMALL>(accB[a].y);
+    AB::store(PB, j, PB[j] + to_torus<SMALL>(accB[a].x));
+    AB::store(PB, j + M, PB[j + M] + to_torus<SMALL>(accB[a].y));
   }
 }
 
 template <int LOGN>
 constexpr size_t br_smem_bytes(int n) {
-  return (size_t)8 * (1 << LOGN) /*acc*/ + (size_t)br_nbuf(LOGN) * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [NBUF][EXW][M]*/ +
-         (size_t)(TFHE_BR_CPASYNC ? 2 * (1 << (LOGN - 1)) * 16 : 0) /*thread-private key stage*/ +
+  return (size_t)8 * TFHE_BR_ACC_EXT * (1 << LOGN) /*acc*/ + (size_t)br_nbuf(LOGN) * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [NBUF][EXW][M]*/ +
          (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
 }
 
+// acquire / release on the per-gate progress words of the work-item hand-over
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
-// The kernel: grid = count gates, block = T = N/16 threads.
+// The throughput kernel: PERSISTENT blocks of T = N/16 threads (as many as are resident at once) take work items from
+// a global counter.  A work item is `chunk_steps` consecutive CMUX steps of one gate; the items of one gate run in
+// order (possibly on different SMs), handing the accumulator TRLWE over through `scratch` in global memory (8 KiB per
+// item at N = 1024, L2-resident).  Items are numbered chunk-major — item = chunk * count + gate — so the predecessor
+// of an item was handed out `count` items earlier and is long finished when the batch exceeds the resident blocks; the
+// acquire on `progress[gate]` makes that a guarantee instead of an assumption.  With nchunks = 1 a work item is a
+// whole gate and nothing is handed over.  Why: a 4096-gate batch is 6.9 waves of 592 resident gates; whole-gate
+// scheduling leaves SMs part-empty for the last wave, 50-step items leave them part-empty for 1/14 of a wave.
+// ctl[0] (next item), ctl[1] (finished blocks) and progress[] must be zero at launch; the last block to finish
+// re-zeroes them, so back-to-back launches need no memset.
 // ---------------------------------------------------------------------------------------------
 // TFHE_BR_LB_THREADS / TFHE_BR_LB_BLOCKS: experiment knob — declare looser launch bounds than the real block size to
 // steer ptxas to a register budget between the (64,4) -> 255 and (64,5) -> 168 choices, e.g. (160,2) -> ~200.
@@ -688,77 +688,98 @@ constexpr size_t br_smem_bytes(int n) {
 template <int LOGN, int L, int BGBIT, bool SMALL, int MINB, bool TEX = false>
 __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(const BrArgs A) {
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
+  using AB = AccBuf<LOGN>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                    // [2][N]
-  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);               // [2][EXW][M]
-  double2* kstage = reinterpret_cast<double2*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M);  // [16][T] if TFHE_BR_CPASYNC
-  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * N + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M + (TFHE_BR_CPASYNC ? 32 * M : 0));
+  uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                                 // [2][EXT * N]
+  double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * AB::STRIDE);                   // [NBUF][EXW][M]
+  unsigned short* abar = reinterpret_cast<unsigned short*>(smem_raw + 8 * AB::STRIDE + 16 * br_nbuf(LOGN) * TFHE_BR_EXW * M);
+  __shared__ unsigned int s_item;
   const int tau = threadIdx.x;
-  const long long g = blockIdx.x;
   const int n = A.n;
-  const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
-
-  // mod switch (evaluator.go:116,122): a~_i = ((a_i + 2^(30-NBIT)) mod 2^32) >> (31-NBIT)
-  for (int i = tau; i < n; i += T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
-  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
-  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
-  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
-  {  // acc = X^btil * testvec
-    for (int j = tau; j < N; j += T) {
-      const int idx = (j - btil) & (2 * N - 1);
-      const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
-      acc[j] = (idx & N) ? ~va : va;
-      acc[N + j] = (idx & N) ? ~vb : vb;
-    }
-  }
+  const unsigned long long total = (unsigned long long)A.count * (unsigned)A.nchunks;
   Fft<LOGN - 1> fft;
   fft.init(ex, A.tw_tab, tau);
-  __syncthreads();
-
   const size_t row_stride = (size_t)2 * L * 2 * M;
-  double2 kA[8], kB[8];
-  int pref = -1;  // step whose first-digit rows are already in kA/kB
-  for (int i = 0; i < n; i++) {
-    const int at = abar[i];
-    if (at == 0) continue;  // X^0: ct1 - ct0 = 0, digits are all zero, the step is an exact no-op
-    if constexpr (TEX)
-      cmux_rotate_step<LOGN, L, BGBIT, SMALL, false>(acc, fft, KeyTex{A.bsk_tex, (int)(row_stride * i)}, at, A.offset, A.tw0, kA, kB);
-    else if constexpr (TFHE_BR_CPASYNC) {
-      const KeyStage bk{A.bsk + row_stride * i, kstage + tau};
-      if (pref != i) {  // first step, or the one after a skipped step: (re)stage the first digit
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + e * T)), "l"(bk.p + tau + e * T) : "memory");
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(bk.st + (8 + e) * T)), "l"(bk.p + M + tau + e * T) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      }
-      cmux_rotate_step<LOGN, L, BGBIT, SMALL, false>(acc, fft, bk, at, A.offset, A.tw0, kA, kB);
-      pref = i + 1;
-    } else if constexpr (TFHE_BR_KPIPE) {
-      const KeyLdg bk{A.bsk + row_stride * i};
-      if (pref != i) {  // first step, or the one after a skipped step
-#pragma unroll
-        for (int e = 0; e < 8; e++) { kA[e] = bk(tau + e * T); kB[e] = bk(M + tau + e * T); }
-      }
-      cmux_rotate_step<LOGN, L, BGBIT, SMALL, true>(acc, fft, bk, at, A.offset, A.tw0, kA, kB);
-      pref = i + 1;  // the last MAC loaded the first rows of step i + 1 (the key buffer has slack past step n - 1)
-    } else
-      cmux_rotate_step<LOGN, L, BGBIT, SMALL, false>(acc, fft, KeyLdg{A.bsk + row_stride * i}, at, A.offset, A.tw0, kA, kB);
+
+  for (;;) {
+    if (tau == 0) s_item = atomicAdd(&A.ctl[0], 1u);
     __syncthreads();
+    const unsigned long long item = s_item;
+    if (item >= total) break;
+    const int chunk = (int)(item / (unsigned long long)A.count);
+    const long long g = (long long)(item - (unsigned long long)chunk * (unsigned long long)A.count);
+    const int i0 = chunk * A.chunk_steps, i1 = min(n, i0 + A.chunk_steps);
+    const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
+    // mod switch (evaluator.go:116,122): a~_i = ((a_i + 2^(30-NBIT)) mod 2^32) >> (31-NBIT)
+    for (int i = i0 + tau; i < i1; i += T) abar[i - i0] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
+    if (chunk == 0) {  // acc = X^btil * testvec, b~ = 2N - ((int64(b) + 2^(30-NBIT)) >> (31-NBIT))
+      const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
+      const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
+      const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+      for (int j = tau; j < N; j += T) {
+        const int idx = (j - btil) & (2 * N - 1);
+        const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
+        AB::store(acc, j, (idx & N) ? ~va : va);
+        AB::store(acc + AB::STRIDE, j, (idx & N) ? ~vb : vb);
+      }
+    } else {  // continue a gate: wait for its previous item, then fetch the accumulator (L2 only: another SM wrote it)
+      if (tau == 0)
+        while (ld_acquire_gpu(A.progress + g) < chunk) __nanosleep(200);
+      __syncthreads();
+      const uint4* src = reinterpret_cast<const uint4*>(A.scratch + g * (2 * N));
+      for (int q = tau; q < 2 * N / 4; q += T) {
+        const uint4 v = __ldcg(src + q);
+        uint32_t* P = acc + (4 * q >= N ? AB::STRIDE - N : 0);
+        AB::store(P, 4 * q + 0, v.x); AB::store(P, 4 * q + 1, v.y); AB::store(P, 4 * q + 2, v.z); AB::store(P, 4 * q + 3, v.w);
+      }
+    }
+    __syncthreads();
+
+    for (int i = i0; i < i1; i++) {
+      const int at = abar[i - i0];
+      if (at == 0) continue;  // X^0: ct1 - ct0 = 0, digits are all zero, the step is an exact no-op
+      if constexpr (TEX)
+        cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyTex{A.bsk_tex, (int)(row_stride * i)}, at, A.offset, A.tw0);
+      else
+        cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyLdg{A.bsk + row_stride * i}, at, A.offset, A.tw0);
+      __syncthreads();
+    }
+
+    if (chunk + 1 < A.nchunks) {  // hand the accumulator to whoever takes the gate's next item
+      uint4* dst = reinterpret_cast<uint4*>(A.scratch + g * (2 * N));
+      for (int q = tau; q < 2 * N / 4; q += T) {
+        const uint32_t* P = acc + (4 * q >= N ? AB::STRIDE - N : 0) + 4 * q;
+        __stcg(dst + q, make_uint4(P[0], P[1], P[2], P[3]));
+      }
+      __threadfence();
+      __syncthreads();
+      if (tau == 0) st_release_gpu(A.progress + g, chunk + 1);
+    } else if (A.out_mode == 0) {
+      uint32_t* o = A.out + g * (2 * N);
+      for (int j = tau; j < N; j += T) { o[j] = acc[j]; o[N + j] = acc[AB::STRIDE + j]; }
+    } else {  // sample extract at 0 (trlwe_ops.go:10-21): out[0] = A[0], out[i] = ~A[N-i], out[N] = B[0]
+      uint32_t* o = A.out + g * (N + 1);
+      for (int j = tau; j < N; j += T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
+      if (tau == 0) o[N] = acc[AB::STRIDE];
+    }
+    __syncthreads();  // acc / abar / s_item are rewritten by the next item
   }
 
-  if (A.out_mode == 0) {
-    uint32_t* o = A.out + g * (2 * N);
-    for (int j = tau; j < 2 * N; j += T) o[j] = acc[j];
-  } else {  // sample extract at 0 (trlwe_ops.go:10-21): out[0] = A[0], out[i] = ~A[N-i], out[N] = B[0]
-    uint32_t* o = A.out + g * (N + 1);
-    for (int j = tau; j < N; j += T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
-    if (tau == 0) o[N] = acc[N];
+  // last block out re-arms the control words for the next launch
+  __syncthreads();
+  if (tau == 0) {
+    __threadfence();
+    s_item = (atomicAdd(&A.ctl[1], 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_item) {
+    if (A.nchunks > 1)
+      for (long long q = tau; q < A.count; q += T) A.progress[q] = 0;
+    if (tau == 0) { A.ctl[0] = 0u; A.ctl[1] = 0u; }
   }
 }
 
+#if TFHE_EXPERIMENTAL
 // =============================================================================================
 // TMA-staged variant: the bootstrapping-key row-set of the current (step, digit) is brought into shared memory by
 // one bulk asynchronous copy (cp.async.bulk -> SASS UBLKCP, completion on an mbarrier) issued by one thread a
@@ -857,8 +878,8 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_staged_k
         const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
         for (int a = 0; a < 8; a++) {
-          x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-          x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+          x[a].x = digit_scaled<BGBIT>(dre[a], sh);
+          x[a].y = digit_scaled<BGBIT>(dim[a], sh);
         }
         // The block barrier inside the first exchange proves every thread has finished the MAC of job q-1, whose
         // buffer ((q+1) & 1) is therefore free: stage job q+1 into it, one whole transform ahead of its use.
@@ -907,6 +928,8 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) blind_rotate_staged_k
     if (tau == 0) o[N] = acc[N];
   }
 }
+
+#endif  // TFHE_EXPERIMENTAL
 
 // ---------------------------------------------------------------------------------------------
 // Stand-alone polynomial transforms in the REFERENCE's FourierPoly layout (groups of 4 real + 4 imaginary parts,
@@ -1028,8 +1051,8 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const Cmu
       const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
       for (int a = 0; a < 8; a++) {
-        x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-        x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+        x[a].x = digit_scaled<BGBIT>(dre[a], sh);
+        x[a].y = digit_scaled<BGBIT>(dim[a], sh);
       }
       fft.forward(x, A.tw0);
       const double2* __restrict__ rowA = A.bsk_row + ((poly * L + lvl) * 2 + 0) * M + tau;

@@ -99,8 +99,8 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
       double2 x[8];
 #pragma unroll
       for (int a = 0; a < 8; a++) {
-        x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-        x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+        x[a].x = digit_scaled<BGBIT>(dre[a], sh);
+        x[a].y = digit_scaled<BGBIT>(dim[a], sh);
       }
       fft.forward(x, A.tw0);
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_latp_ke
       const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
       for (int a = 0; a < 8; a++) {
-        xs[lvl][a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-        xs[lvl][a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+        xs[lvl][a].x = digit_scaled<BGBIT>(dre[a], sh);
+        xs[lvl][a].y = digit_scaled<BGBIT>(dim[a], sh);
       }
       fft.forward(xs[lvl], A.tw0);
     }
@@ -387,8 +387,8 @@ __global__ void __launch_bounds__(2 * L * (1 << (LOGN - 4)), 1) blind_rotate_lat
         const int j = tau + T * a;
         const uint32_t wre = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
         const uint32_t wim = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
-        x[a].x = field_to_double((wre >> sh) & MASK, BIAS);
-        x[a].y = field_to_double((wim >> sh) & MASK, BIAS);
+        x[a].x = digit_scaled<BGBIT>(wre, sh);
+        x[a].y = digit_scaled<BGBIT>(wim, sh);
       }
     }
     fft.forward(x, A.tw0);
@@ -526,8 +526,8 @@ __global__ void __cluster_dims__(2 * L, 1, 1) __launch_bounds__((1 << (LOGN - 4)
         const int j = tau + T * a;
         const uint32_t wre = rot_read<N>(P, ib + T * a) - P[j] + A.offset;
         const uint32_t wim = rot_read<N>(P, ib + T * a + M) - P[j + M] + A.offset;
-        x[a].x = field_to_double((wre >> sh) & MASK, BIAS);
-        x[a].y = field_to_double((wim >> sh) & MASK, BIAS);
+        x[a].x = digit_scaled<BGBIT>(wre, sh);
+        x[a].y = digit_scaled<BGBIT>(wim, sh);
       }
     }
     fft.forward(x, A.tw0);

@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(G * (1 << (LOGN - 4)), 6 / G) blind_rotate_mg_
           double2 x[8];
 #pragma unroll
           for (int a = 0; a < 8; a++) {
-            x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-            x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+            x[a].x = digit_scaled<BGBIT>(dre[a], sh);
+            x[a].y = digit_scaled<BGBIT>(dim[a], sh);
           }
           fft.forward(x, A.tw0);
           mbar_wait(&full[q & 1], (uint32_t)(q >> 1) & 1u);

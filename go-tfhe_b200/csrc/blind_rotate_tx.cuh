@@ -255,8 +255,8 @@ __global__ void __launch_bounds__(64, MINB) blind_rotate_tx_kernel(const BrArgs 
         const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
         for (int a = 0; a < 8; a++) {
-          x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-          x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+          x[a].x = digit_scaled<BGBIT>(dre[a], sh);
+          x[a].y = digit_scaled<BGBIT>(dim[a], sh);
         }
         fft.forward(x, A.tw0);
         const double2* __restrict__ rowA = bk + (size_t)((poly * L + lvl) * 2) * M;
@@ -402,8 +402,8 @@ __global__ void __launch_bounds__(64, MINB) blind_rotate_txs_kernel(const BrArgs
         const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
         for (int a = 0; a < 8; a++) {
-          x[a].x = field_to_double((dre[a] >> sh) & MASK, BIAS);
-          x[a].y = field_to_double((dim[a] >> sh) & MASK, BIAS);
+          x[a].x = digit_scaled<BGBIT>(dre[a], sh);
+          x[a].y = digit_scaled<BGBIT>(dim[a], sh);
         }
         fft.forward(x, A.tw0, [&]() { if (tau == 0 && q + 1 < njobs) issue(q + 1); });
         mbar_wait(&full[q & 1], (uint32_t)(q >> 1) & 1u);

@@ -200,10 +200,13 @@ __global__ void zero_out_rows_kernel(uint32_t* __restrict__ out, int n, const Ga
   for (int w = threadIdx.x; w <= n; w += blockDim.x) out[orow * (n + 1) + w] = 0u;
 }
 
-// ksk [rows][n+1] -> [rows][stride], zero padded
-__global__ void ksk_repack_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int n1, int stride) {
+// ksk [rows][n+1] -> [rows][stride], zero padded.  Rows with digit k = 0 (row index a multiple of base) are never read by
+// the reference (trgsw/keyswitch.go:30 `if k != 0`); they are stored as zeros so that every evaluation order of the
+// key switch (compacted gather, ordered split gather, tensor-core contraction) agrees whatever the caller uploaded there.
+__global__ void ksk_repack_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int n1, int stride, int base) {
   const size_t r = blockIdx.x;
-  for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[r * stride + i] = (i < n1) ? src[r * n1 + i] : 0u;
+  const bool k0 = (r % (size_t)base) == 0;
+  for (int i = threadIdx.x; i < stride; i += blockDim.x) dst[r * stride + i] = (i < n1 && !k0) ? src[r * n1 + i] : 0u;
 }
 
 // Bootstrapping key: reference FourierPoly layout -> engine layout.
@@ -211,10 +214,14 @@ __global__ void ksk_repack_kernel(const uint32_t* __restrict__ src, uint32_t* __
 //        re at (k/4)*8 + k%4 and im at (k/4)*8 + 4 + k%4   (poly/poly.go:54-62)
 //   dst: [polys][8][T] double2, spectrum position k = 8*tau + e stored at [e][tau], scaled by 1/M
 //        (the inverse transform's 1/(N/2), fourier_transform.go:318-346; a power of two, exact).
-__global__ void bsk_repack_kernel(const double* __restrict__ src, double2* __restrict__ dst, int N) {
+__global__ void bsk_repack_kernel(const double* __restrict__ src, double2* __restrict__ dst, int N, int L, int bgbit) {
   const int M = N / 2, T = M / 8;
-  const size_t poly = blockIdx.x;
-  const double scale = 1.0 / (double)M;
+  const size_t poly = blockIdx.x;  // ((step * 2L + row) * 2 + {A,B})
+  // 2/N: the inverse transform's scale.  2^-sh: the digits of level (row mod L) reach the transform scaled by 2^sh
+  // (digit_scaled, blind_rotate.cuh); both are powers of two, so every product keeps the reference's exact value.
+  const int lvl = (int)((poly / 2) % (size_t)(2 * L)) % L;
+  double scale = 1.0 / (double)M;
+  for (int k = 0; k < 32 - (lvl + 1) * bgbit; k++) scale *= 0.5;
   for (int k = threadIdx.x; k < M; k += blockDim.x) {
     const double re = src[poly * N + (k >> 2) * 8 + (k & 3)];
     const double im = src[poly * N + (k >> 2) * 8 + 4 + (k & 3)];

@@ -16,11 +16,20 @@
 #include <string>
 #include <vector>
 
+// TFHE_EXPERIMENTAL: also builds the measured-slower blind-rotate variants of round 1 (TMA-staged / texture key fetch,
+// TMEM accumulators, TMEM exchange, warp-per-gate, gates-per-block, per-digit and cluster latency kernels; see
+// profiles/r01_experiments.md).  The default library holds only what the engine selects by itself: the throughput
+// kernel, the two latency kernels (lat, latp), both key-switch kernels and key generation.
+#ifndef TFHE_EXPERIMENTAL
+#define TFHE_EXPERIMENTAL 0
+#endif
 #include "blind_rotate.cuh"
+#if TFHE_EXPERIMENTAL
 #include "blind_rotate_w16.cuh"
 #include "blind_rotate_tx.cuh"
 #include "blind_rotate_tms.cuh"
 #include "blind_rotate_mg.cuh"
+#endif
 #include "blind_rotate_lat.cuh"
 #include "lwe_kernels.cuh"
 #include "key_switch_mma.cuh"
@@ -78,6 +87,10 @@ struct tfhe_ctx {
   DevBuf h2d_a, h2d_b, h2d_c, h2d_luts, d2h_out;              // staging for the host-buffer API
   int64_t launches = 0;
   int sm_count = 0;
+  // persistent throughput kernel: resident blocks per SM, control words (ctl[2] + progress[]) and accumulator hand-over
+  int br_blocks_per_sm = 1;
+  int br_chunk_steps = 0;    // 0 = automatic (launch_blind_rotate), else CMUX steps per work item (>= n: whole gates)
+  DevBuf br_ctl, br_scratch;
   std::string err;
   // optional per-stage timing (tfhe_ctx_set_timing): CUDA events on the launching stream
   // how blind rotate reads the key rows: 0 = LDG straight from L2 (default, fastest measured), 1 = TMA-staged through
@@ -86,10 +99,12 @@ struct tfhe_ctx {
   bool br_auto_cl = false;   // variant 0 may also pick the cluster kernel for a handful of gates (set once measured)
   bool br_auto_lat = true;   // variant 0 picks the latency kernel for batches of <= 2 gates per SM (exact parameter sets)
   cudaTextureObject_t bsk_tex = 0;
+#if TFHE_EXPERIMENTAL
   // warp-per-gate kernel (N = 1024 only): its own key layout and twiddle tables
   double2* d_bsk16 = nullptr;
   double2* d_tw16 = nullptr;   // [8][16] pass-1 twiddles then [4][32] last-stage twiddles
   Tw8 tw0_16{};
+#endif
   bool timing = false;
   struct StageEv { cudaEvent_t e0, e1, e2; };
   std::vector<StageEv> ev_live, ev_free;
@@ -149,11 +164,16 @@ void build_twiddles(Tw4& tw0, std::vector<Tw4>& tab) {
 struct Variant {
   int logN, L, bgbit;
   bool small;
-  void (*br)(const BrArgs);          // key rows read straight from L2 (LDG)
-  void (*br_tex)(const BrArgs);      // key rows fetched through the texture pipe
-  void (*br_staged)(const BrArgs);   // key rows TMA-staged into shared memory (cp.async.bulk + mbarrier)
+  void (*br)(const BrArgs);          // throughput kernel: block per gate, key rows read straight from L2 (LDG)
   void (*cmux)(const CmuxArgs);
   size_t (*br_smem)(int n);
+  void (*br_lat)(const BrArgs);      // latency mode: 4 warps per gate, the two polynomials in parallel (exact sets, N = 1024)
+  size_t (*br_lat_smem)(int n);
+  void (*br_latp)(const BrArgs);     // latency mode that keeps the reference's accumulation order (L <= 2: the Uint / PBS sets)
+  size_t (*br_latp_smem)(int n);
+#if TFHE_EXPERIMENTAL
+  void (*br_tex)(const BrArgs);      // key rows fetched through the texture pipe
+  void (*br_staged)(const BrArgs);   // key rows TMA-staged into shared memory (cp.async.bulk + mbarrier)
   size_t (*br_staged_smem)(int n);
   void (*br_w16)(const BrW16Args);   // warp-per-gate, TMEM accumulators (N = 1024 only, else nullptr)
   void (*br_tm)(const BrArgs);       // block-per-gate, TMEM accumulators (N >= 1024, else nullptr)
@@ -163,21 +183,12 @@ struct Variant {
   size_t (*br_tms_smem)(int n);
   void (*br_mg)(const BrArgs, long long);  // G gates per block sharing one staged copy of the key rows, TMEM accumulators (N = 1024)
   size_t (*br_mg_smem)(int n);
-  void (*br_lat)(const BrArgs);      // latency mode: 4 warps per gate, the two polynomials in parallel (exact sets, N = 1024)
-  size_t (*br_lat_smem)(int n);
   void (*br_lat2)(const BrArgs);     // latency mode, one group per digit (2L x N/16 threads): <= 1 gate per SM
   size_t (*br_lat2_smem)(int n);
-  void (*br_latp)(const BrArgs);     // latency mode that keeps the reference's accumulation order (L <= 2: the Uint / PBS sets)
-  size_t (*br_latp_smem)(int n);
   void (*br_cl)(const BrArgs);       // one gate on a cluster of 2L blocks (one SM per digit, DSMEM): a handful of gates
   size_t (*br_cl_smem)(int n);
+#endif
 };
-template <int LOGN, int L, int BG, bool SMALL>
-constexpr auto cl_kernel() -> void (*)(const BrArgs) {
-  if constexpr (LOGN == 10 && SMALL && 2 * L <= 8) return blind_rotate_cl_kernel<LOGN, L, BG, SMALL>;
-  else return nullptr;
-}
-template <int LOGN> size_t br_cl_smem(int n) { return br_cl_smem_bytes<LOGN>(n); }
 template <int LOGN, int L, int BG, bool SMALL>
 constexpr auto latp_kernel() -> void (*)(const BrArgs) {
   if constexpr (L <= 2) return blind_rotate_latp_kernel<LOGN, L, BG, SMALL>;
@@ -185,17 +196,25 @@ constexpr auto latp_kernel() -> void (*)(const BrArgs) {
 }
 template <int LOGN, int L> size_t br_latp_smem(int n) { return br_latp_smem_bytes<LOGN, (L <= 2 ? L : 1)>(n); }
 template <int LOGN, int L, int BG, bool SMALL>
-constexpr auto lat2_kernel() -> void (*)(const BrArgs) {
-  if constexpr (LOGN == 10 && SMALL) return blind_rotate_lat2_kernel<LOGN, L, BG, SMALL>;
-  else return nullptr;
-}
-template <int LOGN, int L> size_t br_lat2_smem(int n) { return br_lat2_smem_bytes<LOGN, L>(n); }
-template <int LOGN, int L, int BG, bool SMALL>
 constexpr auto lat_kernel() -> void (*)(const BrArgs) {
   if constexpr (LOGN == 10 && SMALL) return blind_rotate_lat_kernel<LOGN, L, BG, SMALL>;
   else return nullptr;
 }
 template <int LOGN> size_t br_lat_smem(int n) { return br_lat_smem_bytes<LOGN>(n); }
+template <int LOGN> size_t br_smem(int n) { return br_smem_bytes<LOGN>(n); }
+#if TFHE_EXPERIMENTAL
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto cl_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10 && SMALL && 2 * L <= 8) return blind_rotate_cl_kernel<LOGN, L, BG, SMALL>;
+  else return nullptr;
+}
+template <int LOGN> size_t br_cl_smem(int n) { return br_cl_smem_bytes<LOGN>(n); }
+template <int LOGN, int L, int BG, bool SMALL>
+constexpr auto lat2_kernel() -> void (*)(const BrArgs) {
+  if constexpr (LOGN == 10 && SMALL) return blind_rotate_lat2_kernel<LOGN, L, BG, SMALL>;
+  else return nullptr;
+}
+template <int LOGN, int L> size_t br_lat2_smem(int n) { return br_lat2_smem_bytes<LOGN, L>(n); }
 #ifndef TFHE_BR_MG_G
 #define TFHE_BR_MG_G 6
 #endif
@@ -214,7 +233,6 @@ constexpr auto tms_kernel() -> void (*)(const BrArgs) {
   else return nullptr;
 }
 template <int LOGN> size_t br_tms_smem(int n) { return br_tms_smem_bytes<LOGN>(n); }
-template <int LOGN> size_t br_smem(int n) { return br_smem_bytes<LOGN>(n); }
 template <int LOGN> size_t br_staged_smem(int n) { return br_staged_smem_bytes<LOGN>(n); }
 #ifndef TFHE_BR_W16_MINB
 #define TFHE_BR_W16_MINB 2
@@ -249,15 +267,19 @@ constexpr auto tm_kernel() -> void (*)(const BrArgs) {
 #ifndef TFHE_BR_STAGED_MINB_N1024
 #define TFHE_BR_STAGED_MINB_N1024 4
 #endif
-#define VARIANT(LOGN, L, BG, SMALL, MINB, MINBS)                                                    \
-  { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>,                              \
-    blind_rotate_kernel<LOGN, L, BG, SMALL, MINB, true>,                                            \
-    blind_rotate_staged_kernel<LOGN, L, BG, SMALL, MINBS>, cmux_kernel<LOGN, L, BG, SMALL, MINB>,   \
-    br_smem<LOGN>, br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>(),           \
-    tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>(), tms_kernel<LOGN, L, BG, SMALL>(), br_tms_smem<LOGN>,  \
-    mg_kernel<LOGN, L, BG, SMALL>(), br_mg_smem<LOGN>, lat_kernel<LOGN, L, BG, SMALL>(), br_lat_smem<LOGN>,  \
-    lat2_kernel<LOGN, L, BG, SMALL>(), br_lat2_smem<LOGN, L>, latp_kernel<LOGN, L, BG, SMALL>(), br_latp_smem<LOGN, L>,  \
-    cl_kernel<LOGN, L, BG, SMALL>(), br_cl_smem<LOGN> }
+#define VARIANT_EXP(LOGN, L, BG, SMALL, MINB, MINBS)                                                                  \
+  , blind_rotate_kernel<LOGN, L, BG, SMALL, MINB, true>, blind_rotate_staged_kernel<LOGN, L, BG, SMALL, MINBS>,        \
+    br_staged_smem<LOGN>, w16_kernel<LOGN, L, BG, SMALL>(), tm_kernel<LOGN, L, BG, SMALL>(),                           \
+    tx_kernel<LOGN, L, BG, SMALL>(), txs_kernel<LOGN, L, BG, SMALL>(), tms_kernel<LOGN, L, BG, SMALL>(), br_tms_smem<LOGN>, \
+    mg_kernel<LOGN, L, BG, SMALL>(), br_mg_smem<LOGN>, lat2_kernel<LOGN, L, BG, SMALL>(), br_lat2_smem<LOGN, L>,        \
+    cl_kernel<LOGN, L, BG, SMALL>(), br_cl_smem<LOGN>
+#else
+#define VARIANT_EXP(LOGN, L, BG, SMALL, MINB, MINBS)
+#endif
+#define VARIANT(LOGN, L, BG, SMALL, MINB, MINBS)                                                     \
+  { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>, cmux_kernel<LOGN, L, BG, SMALL, MINB>, \
+    br_smem<LOGN>, lat_kernel<LOGN, L, BG, SMALL>(), br_lat_smem<LOGN>, latp_kernel<LOGN, L, BG, SMALL>(),     \
+    br_latp_smem<LOGN, L> VARIANT_EXP(LOGN, L, BG, SMALL, MINB, MINBS) }
 #ifndef TFHE_BR_MINB_N1024
 #define TFHE_BR_MINB_N1024 4
 #endif
@@ -286,6 +308,30 @@ int set_device(tfhe_ctx* c) {
 }
 
 // --- engine steps on device buffers --------------------------------------------------------------
+// Work-item size of the persistent throughput kernel.  A batch that fits the resident blocks runs whole gates (nothing to
+// balance).  Larger batches are cut into items of ~n/14 steps, the count in [10, 20] chosen so that the LAST round of
+// items over the resident blocks is as full as possible (4096 gates at n = 700 over 592 blocks: 13 items of 54 steps =
+// 89.95 rounds).
+void pick_chunks(const tfhe_ctx* c, int64_t count, int* nchunks, int* chunk_steps) {
+  const int n = c->P.n;
+  const int64_t resident = (int64_t)c->sm_count * c->br_blocks_per_sm;
+  *nchunks = 1; *chunk_steps = n;
+  if (c->br_chunk_steps > 0) {
+    *chunk_steps = std::min(n, c->br_chunk_steps);
+    *nchunks = (n + *chunk_steps - 1) / *chunk_steps;
+    return;
+  }
+  if (count <= resident || n < 64) return;
+  double best = 1e300;
+  for (int k = 10; k <= 20; k++) {
+    const int steps = (n + k - 1) / k;
+    const int kk = (n + steps - 1) / steps;
+    const double rounds = (double)count * kk / (double)resident;
+    const double cost = std::ceil(rounds) / rounds * (1.0 + 0.0005 * kk);  // last-round fill, small per-item overhead
+    if (cost < best) { best = cost; *nchunks = kk; *chunk_steps = steps; }
+  }
+}
+
 int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const uint32_t* d_luts, int64_t nluts,
                         uint32_t* d_out, int out_mode, cudaStream_t s) {
   if (count == 0) return 0;
@@ -293,7 +339,9 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   BrArgs a{};
   a.ct_in = d_ct; a.testvec = c->d_testvec; a.luts = d_luts; a.nluts = nluts; a.bsk = c->d_bsk; a.tw_tab = c->d_tw;
   a.out = d_out; a.n = c->P.n; a.offset = c->offset; a.out_mode = out_mode; a.tw0 = c->tw0;
+  a.count = count; a.nchunks = 1; a.chunk_steps = c->P.n;
   const int T = c->P.N / 16;
+#if TFHE_EXPERIMENTAL
   if (c->br_variant == 3 && V.br_w16 && c->d_bsk16) {
     BrW16Args w{};
     w.ct_in = d_ct; w.testvec = c->d_testvec; w.luts = d_luts; w.nluts = nluts; w.count = count; w.bsk = c->d_bsk16;
@@ -305,29 +353,72 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
     return 0;
   }
   a.bsk_tex = c->bsk_tex;
+  bool done = true;
   if (c->br_variant == 6 && V.br_txs) V.br_txs<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 5 && V.br_tx) V.br_tx<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
-  // latency mode with one 64-thread group per digit (2L groups): explicit choice only
-  // a handful of gates: one cluster of 2L blocks (2L SMs) per gate
-  else if (V.br_cl && (c->br_variant == 13 || (c->br_variant == 0 && c->br_auto_lat && c->br_auto_cl && count <= (int64_t)c->sm_count / (2 * c->P.L) / 2)))
-    V.br_cl<<<(unsigned)(count * 2 * c->P.L), T, V.br_cl_smem(c->P.n), s>>>(a);
-  // order-preserving latency mode (Uint / PBS sets): a batch of at most one ciphertext per SM
-  else if (V.br_latp && (c->br_variant == 12 || (c->br_variant == 0 && c->br_auto_lat && count <= (int64_t)c->sm_count)))
-    V.br_latp<<<(unsigned)count, 2 * T, V.br_latp_smem(c->P.n), s>>>(a);
-  else if (V.br_lat2 && c->br_variant == 11)  // measured: not faster than the two-group kernel below, so never picked automatically
-    V.br_lat2<<<(unsigned)count, 2 * c->P.L * T, V.br_lat2_smem(c->P.n), s>>>(a);
-  // latency mode: a batch that cannot fill the SMs with the throughput kernel (<= 2 gates per SM) gets four warps per gate
-  else if (V.br_lat && (c->br_variant == 9 || (c->br_variant == 0 && c->br_auto_lat && count <= 2 * (int64_t)c->sm_count)))
-    V.br_lat<<<(unsigned)count, 2 * T, V.br_lat_smem(c->P.n), s>>>(a);
+  else if (V.br_cl && c->br_variant == 13) V.br_cl<<<(unsigned)(count * 2 * c->P.L), T, V.br_cl_smem(c->P.n), s>>>(a);
+  else if (V.br_lat2 && c->br_variant == 11) V.br_lat2<<<(unsigned)count, 2 * c->P.L * T, V.br_lat2_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 8 && V.br_mg)
     V.br_mg<<<(unsigned)((count + TFHE_BR_MG_G - 1) / TFHE_BR_MG_G), TFHE_BR_MG_G * T, V.br_mg_smem(c->P.n), s>>>(a, (long long)count);
   else if (c->br_variant == 7 && V.br_tms) V.br_tms<<<(unsigned)count, T, V.br_tms_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 4 && V.br_tm) V.br_tm<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
   else if (c->br_variant == 1) V.br_staged<<<(unsigned)count, T, V.br_staged_smem(c->P.n), s>>>(a);
-  else if (c->br_variant == 2) V.br_tex<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
-  else V.br<<<(unsigned)count, T, V.br_smem(c->P.n), s>>>(a);
-  c->launches++;
-  CK(c, cudaGetLastError());
+  else done = false;
+  if (done) {
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+  }
+#endif
+  // order-preserving latency mode (Uint / PBS sets): a batch of at most one ciphertext per SM
+  if (V.br_latp && (c->br_variant == 12 || (c->br_variant == 0 && c->br_auto_lat && count <= (int64_t)c->sm_count))) {
+    V.br_latp<<<(unsigned)count, 2 * T, V.br_latp_smem(c->P.n), s>>>(a);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+  }
+  // latency mode: a batch that cannot fill the SMs with the throughput kernel (<= 2 gates per SM) gets four warps per gate
+  if (V.br_lat && (c->br_variant == 9 || (c->br_variant == 0 && c->br_auto_lat && count <= 2 * (int64_t)c->sm_count))) {
+    V.br_lat<<<(unsigned)count, 2 * T, V.br_lat_smem(c->P.n), s>>>(a);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+  }
+  // throughput kernel: persistent blocks over work items, in sub-batches that bound the hand-over buffer
+  const int64_t SUB = 32768;
+  const int64_t resident = (int64_t)c->sm_count * c->br_blocks_per_sm;
+  for (int64_t g0 = 0; g0 < count; g0 += SUB) {
+    const int64_t cnt = std::min<int64_t>(SUB, count - g0);
+    BrArgs b = a;
+    b.count = cnt;
+    b.ct_in = d_ct + (size_t)g0 * (c->P.n + 1);
+    if (d_luts && nluts != 1) b.luts = d_luts + (size_t)g0 * 2 * c->P.N;
+    b.out = d_out + (size_t)g0 * (out_mode == 0 ? 2 * c->P.N : c->P.N + 1);
+    pick_chunks(c, cnt, &b.nchunks, &b.chunk_steps);
+    const size_t ctl_bytes = 16 + (size_t)std::min<int64_t>(SUB, std::max<int64_t>(cnt, 1)) * sizeof(int);
+    if (ctl_bytes > c->br_ctl.cap) {  // (re)allocated control words start at zero; the kernel leaves them at zero
+      CK(c, c->br_ctl.reserve(16 + (size_t)SUB * sizeof(int)));
+      CK(c, cudaMemsetAsync(c->br_ctl.p, 0, c->br_ctl.cap, s));
+    }
+    b.ctl = c->br_ctl.as<unsigned int>();
+    b.progress = reinterpret_cast<int*>(c->br_ctl.as<unsigned char>() + 16);
+    if (b.nchunks > 1) {
+      if (out_mode == 0) b.scratch = b.out;  // the TRLWE output rows double as the hand-over buffer
+      else {
+        CK(c, c->br_scratch.reserve((size_t)cnt * 2 * c->P.N * 4));
+        b.scratch = c->br_scratch.as<uint32_t>();
+      }
+    }
+    const int64_t items = cnt * b.nchunks;
+    const unsigned grid = (unsigned)std::min<int64_t>(items, resident);
+#if TFHE_EXPERIMENTAL
+    if (c->br_variant == 2) V.br_tex<<<grid, T, V.br_smem(c->P.n), s>>>(b);
+    else
+#endif
+    V.br<<<grid, T, V.br_smem(c->P.n), s>>>(b);
+    c->launches++;
+    CK(c, cudaGetLastError());
+  }
   return 0;
 }
 
@@ -510,14 +601,26 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
   const Variant& V = kVariants[v];
-  if (V.br_cl && (e = cudaFuncSetAttribute(V.br_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_cl_smem(4096))) != cudaSuccess)
-    return bail("cudaFuncSetAttribute(blind_rotate_cl)", e);
   if (V.br_latp && (e = cudaFuncSetAttribute(V.br_latp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_latp_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_latp)", e);
-  if (V.br_lat2 && (e = cudaFuncSetAttribute(V.br_lat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat2_smem(2048))) != cudaSuccess)
-    return bail("cudaFuncSetAttribute(blind_rotate_lat2)", e);
   if (V.br_lat && (e = cudaFuncSetAttribute(V.br_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_lat)", e);
+  if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)  // limit, not allocation: n <= 4096
+    return bail("cudaFuncSetAttribute(blind_rotate)", e);
+  {  // resident blocks of the persistent throughput kernel (registers: 4 at N = 1024)
+    int nb = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, V.br, P.N / 16, V.br_smem(P.n))) != cudaSuccess)
+      return bail("cudaOccupancyMaxActiveBlocksPerMultiprocessor(blind_rotate)", e);
+    c->br_blocks_per_sm = nb > 0 ? nb : 1;
+  }
+  if (const char* cs = getenv("TFHE_B200_BR_CHUNK_STEPS")) c->br_chunk_steps = atoi(cs);
+  if (const char* sel = getenv("TFHE_B200_BR"))
+    c->br_variant = !strcmp(sel, "lat") ? 9 : !strcmp(sel, "latp") ? 12 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
+#if TFHE_EXPERIMENTAL
+  if (V.br_cl && (e = cudaFuncSetAttribute(V.br_cl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_cl_smem(4096))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_cl)", e);
+  if (V.br_lat2 && (e = cudaFuncSetAttribute(V.br_lat2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_lat2_smem(2048))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(blind_rotate_lat2)", e);
   if (V.br_mg && (e = cudaFuncSetAttribute(V.br_mg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_mg_smem(2048))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_mg)", e);
   if (V.br_tms && (e = cudaFuncSetAttribute(V.br_tms, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_tms_smem(4096))) != cudaSuccess)
@@ -549,15 +652,14 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
     if ((e = cudaFuncSetAttribute(V.br_w16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)br_w16_smem_bytes(4096))) != cudaSuccess)
       return bail("cudaFuncSetAttribute(blind_rotate_w16)", e);
   }
-  if ((e = cudaFuncSetAttribute(V.br, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)  // limit, not allocation: n <= 4096
-    return bail("cudaFuncSetAttribute(blind_rotate)", e);
   if ((e = cudaFuncSetAttribute(V.br_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_staged_smem(4096))) !=
       cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_staged)", e);
   if ((e = cudaFuncSetAttribute(V.br_tex, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V.br_smem(4096))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(blind_rotate_tex)", e);
   if (const char* sel = getenv("TFHE_B200_BR"))
-    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat") ? 9 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "latp") ? 12 : !strcmp(sel, "cl") ? 13 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
+    c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "cl") ? 13 : c->br_variant;
+#endif
   if (c->br_variant == 10) { c->br_variant = 0; c->br_auto_lat = false; }
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
@@ -577,14 +679,16 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   for (DevBuf* b : {&c->wires, &c->gate_descs, &c->prep, &c->lwe1, &c->tmp, &c->prep2, &c->idx_a, &c->idx_b, &c->ops_dev, &c->h2d_a, &c->h2d_b,
-                    &c->h2d_c, &c->h2d_luts, &c->d2h_out})
+                    &c->h2d_c, &c->h2d_luts, &c->d2h_out, &c->br_ctl, &c->br_scratch})
     b->release();
   for (auto* v : {&c->ev_live, &c->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); cudaEventDestroy(ev.e2); }
   if (c->bsk_tex) cudaDestroyTextureObject(c->bsk_tex);
   if (c->d_bsk) cudaFree(c->d_bsk);
+#if TFHE_EXPERIMENTAL
   if (c->d_bsk16) cudaFree(c->d_bsk16);
   if (c->d_tw16) cudaFree(c->d_tw16);
+#endif
   if (c->d_ksk) cudaFree(c->d_ksk);
   if (c->d_ksk_bytes) cudaFree(c->d_ksk_bytes);
   c->ks_sel.release();
@@ -604,26 +708,29 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
   const int M = P.N / 2;
   if (!c->d_bsk) CK(c, cudaMalloc(&c->d_bsk, polys * M * sizeof(double2) + (size_t)8 * 2 * M * sizeof(double2)));  // + slack for key-row prefetches past the last step
   if (!c->d_testvec) CK(c, cudaMalloc(&c->d_testvec, (size_t)2 * P.N * 4));
-  bsk_repack_kernel<<<(unsigned)polys, 128, 0, s>>>(d_bsk_fft, c->d_bsk, P.N);
+  bsk_repack_kernel<<<(unsigned)polys, 128, 0, s>>>(d_bsk_fft, c->d_bsk, P.N, P.L, P.bgbit);
   c->launches++;
   CK(c, cudaGetLastError());
+#if TFHE_EXPERIMENTAL
   if (kVariants[c->variant].br_w16) {
     if (!c->d_bsk16) CK(c, cudaMalloc(&c->d_bsk16, polys * M * sizeof(double2)));
     bsk_repack_w16_kernel<<<(unsigned)polys, 128, 0, s>>>(d_bsk_fft, c->d_bsk16);
     c->launches++;
     CK(c, cudaGetLastError());
   }
+#endif
   CK(c, cudaMemcpyAsync(c->d_testvec, d_testvec, (size_t)2 * P.N * 4, cudaMemcpyDeviceToDevice, s));
+  c->has_ksk = false;  // a key loaded without a key-switching key must not be paired with the previous one
+  c->ks_K = 0;
   if (d_ksk) {
     const size_t rows = (size_t)P.N * P.iks_t * (1u << P.basebit);
     c->ksk_stride = (P.n + 1 + 3) / 4 * 4;
     if (!c->d_ksk) CK(c, cudaMalloc(&c->d_ksk, rows * c->ksk_stride * 4));
-    ksk_repack_kernel<<<(unsigned)rows, 128, 0, s>>>(d_ksk, c->d_ksk, P.n + 1, c->ksk_stride);
+    ksk_repack_kernel<<<(unsigned)rows, 128, 0, s>>>(d_ksk, c->d_ksk, P.n + 1, c->ksk_stride, 1 << P.basebit);
     c->launches++;
     CK(c, cudaGetLastError());
     c->has_ksk = true;
     // byte planes for the tensor-core key switch: only where the dense product is cheap (base - 1 = 3 rows per digit)
-    c->ks_K = 0;
     const long long K = (long long)P.N * P.iks_t * ((1 << P.basebit) - 1);
     if (P.basebit == 2 && K % KSM_BK == 0 && K <= 160 * 1024 && encode_tiled_fn()) {
       const int cols = 4 * c->ksk_stride;
@@ -638,6 +745,7 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
     }
   }
   CK(c, cudaStreamSynchronize(s));
+#if TFHE_EXPERIMENTAL
   if (!c->bsk_tex) {
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeLinear;
@@ -649,6 +757,7 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
     if (cudaCreateTextureObject(&c->bsk_tex, &rd, &td, nullptr) != cudaSuccess) { c->bsk_tex = 0; cudaGetLastError(); }
   }
   if (c->br_variant == 2 && !c->bsk_tex) return fail(c, TFHE_ERR_CUDA, "texture object over the bootstrapping key failed");
+#endif
   c->offset = offset;
   c->key_loaded = true;
   return TFHE_OK;
@@ -1118,21 +1227,26 @@ int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
 
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (!c) return TFHE_ERR_ARG;
+  if (variant == 0) { c->br_variant = 0; c->br_auto_lat = true; return TFHE_OK; }
   if (variant == 10) { c->br_variant = 0; c->br_auto_lat = false; return TFHE_OK; }  // throughput kernel at every batch size
-  if (variant == 13) {
-    if (!kVariants[c->variant].br_cl) return fail(c, TFHE_ERR_ARG, "the cluster kernel exists for the exact N = 1024 sets only");
-    c->br_variant = 13; c->br_auto_lat = true; return TFHE_OK;
-  }
   if (variant == 12) {
     if (!kVariants[c->variant].br_latp) return fail(c, TFHE_ERR_ARG, "the order-preserving latency kernel exists for L <= 2 only");
     c->br_variant = 12; c->br_auto_lat = true; return TFHE_OK;
+  }
+  if (variant == 9) {
+    if (!kVariants[c->variant].br_lat) return fail(c, TFHE_ERR_ARG, "the latency kernel exists for the exact N = 1024 sets only");
+    c->br_variant = 9; c->br_auto_lat = true; return TFHE_OK;
+  }
+#if TFHE_EXPERIMENTAL
+  if (variant == 13) {
+    if (!kVariants[c->variant].br_cl) return fail(c, TFHE_ERR_ARG, "the cluster kernel exists for the exact N = 1024 sets only");
+    c->br_variant = 13; c->br_auto_lat = true; return TFHE_OK;
   }
   if (variant == 11) {
     if (!kVariants[c->variant].br_lat2 || c->P.n > 2048) return fail(c, TFHE_ERR_ARG, "the per-digit latency kernel exists for the exact N = 1024 sets only");
     c->br_variant = 11; c->br_auto_lat = true; return TFHE_OK;
   }
-  if (variant < 0 || variant > 9) return fail(c, TFHE_ERR_ARG, "variant must be 0 (default), 1 (tma), 2 (tex), 3 (w16), 4 (tmem), 5 (tmex), 6 (tmex+tma), 7 (tms), 8 (mg), 9 (lat) or 10 (ldg at every batch size)");
-  if (variant == 9 && !kVariants[c->variant].br_lat) return fail(c, TFHE_ERR_ARG, "the latency kernel exists for the exact N = 1024 sets only");
+  if (variant < 0 || variant > 8) return fail(c, TFHE_ERR_ARG, "unknown blind-rotate variant %d", variant);
   c->br_auto_lat = true;
   if (variant == 8 && (!kVariants[c->variant].br_mg || c->P.n > 2048)) return fail(c, TFHE_ERR_ARG, "the gates-per-block kernel exists for N = 1024, n <= 2048 only");
   if (variant == 7 && !kVariants[c->variant].br_tms) return fail(c, TFHE_ERR_ARG, "the six-blocks-per-SM kernel exists for N = 1024 only");
@@ -1141,6 +1255,17 @@ int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   if (variant == 3 && !kVariants[c->variant].br_w16) return fail(c, TFHE_ERR_ARG, "the warp-per-gate kernel exists for N = 1024 only");
   if (variant == 2 && c->key_loaded && !c->bsk_tex) return fail(c, TFHE_ERR_STATE, "no texture object");
   c->br_variant = variant;
+  return TFHE_OK;
+#else
+  return fail(c, TFHE_ERR_ARG, "blind-rotate variant %d is an experimental kernel: rebuild with -DTFHE_EXPERIMENTAL=1 "
+                               "(default library: 0 = automatic, 9 = lat, 10 = throughput kernel only, 12 = latp)", variant);
+#endif
+}
+
+// CMUX steps per work item of the persistent throughput kernel: 0 = automatic, >= n = whole gates per item.
+int tfhe_ctx_set_blind_rotate_chunk_steps(tfhe_ctx* c, int steps) {
+  if (!c || steps < 0) return fail(c, TFHE_ERR_ARG, "chunk steps must be >= 0");
+  c->br_chunk_steps = steps;
   return TFHE_OK;
 }
 

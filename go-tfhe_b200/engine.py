@@ -197,9 +197,14 @@ class Context:
                  "tfhe_gate_batch_device")
 
     def set_blind_rotate_variant(self, variant):
-        """'ldg' (default) | 'tma' | 'tex' — how key rows reach the MAC; results are identical."""
+        """'ldg' (automatic, default) | 'throughput' | 'lat' | 'latp'; the other names are round-1 experiments that exist
+        only in a -DTFHE_EXPERIMENTAL=1 build.  Results are identical."""
         v = {"ldg": 0, "tma": 1, "tex": 2, "w16": 3, "tmem": 4, "tmex": 5, "tmex+tma": 6, "tms": 7, "mg": 8, "lat": 9, "throughput": 10, "lat2": 11, "latp": 12, "cl": 13}[variant] if isinstance(variant, str) else int(variant)
         self._ck(self.lib.tfhe_ctx_set_blind_rotate_variant(self.h, v), "tfhe_ctx_set_blind_rotate_variant")
+
+    def set_blind_rotate_chunk_steps(self, steps):
+        """CMUX steps per work item of the persistent throughput kernel (0 = automatic); results do not depend on it."""
+        self._ck(self.lib.tfhe_ctx_set_blind_rotate_chunk_steps(self.h, int(steps)), "tfhe_ctx_set_blind_rotate_chunk_steps")
 
     def set_key_switch_variant(self, variant):
         """'auto' (default) | 'gather' | 'mma' — row gather out of L2 or one tensor-core contraction; results are identical."""

@@ -172,22 +172,19 @@ int tfhe_gate_batch_device(tfhe_ctx* ctx, int64_t count, const uint8_t* d_ops, i
 /* --- introspection ---------------------------------------------------------------------------- */
 /* Number of CUDA kernels this context has launched since creation (bench.py: gpu_launches). */
 int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
-/* Selects the blind-rotate kernel: 0 = block per gate, key rows by LDG straight from L2 (default), 1 = key rows
- * TMA-staged through shared memory (cp.async.bulk + mbarrier), 2 = key rows through the texture pipe, 3 = one warp
- * per gate with 16 points per thread and the spectrum accumulators in tensor memory (N = 1024 only), 4 = block per
- * gate with the accumulators in tensor memory (N >= 1024), 5 = block per gate with the second transform exchange
- * through tensor memory + a lane shuffle (N = 1024), 6 = 5 plus TMA-staged key rows, 7 = six blocks per SM: accumulators
- * in tensor memory + key rows TMA-staged into one shared-memory buffer, 158 registers (N = 1024), 8 = six gates per
- * block sharing one double-buffered staged copy of the key rows (N = 1024), 9 = latency mode: four warps per gate, the
- * two polynomials of a CMUX step in parallel (80/110/128-bit sets; variant 0 switches to it on its own for batches of at
- * most two gates per SM), 10 = variant 0 without that switch, 11 = latency mode with one 64-thread group per digit (2L
- * groups; measured no faster than 9, explicit choice only), 12 = latency mode for the L <= 2 sets (Uint1-5 / programmable
- * bootstraps): two groups transform the two polynomials concurrently and pass the accumulation chain on in the reference's
- * row order, bit-identical for every set; variant 0 uses it for at most one ciphertext per SM, 13 = one gate on a thread-block
- * cluster of 2L blocks (one SM per digit, partial products through distributed shared memory; exact N = 1024 sets;
- * measured no faster than 9, explicit choice only).  All compute identical results;
- * the default is the fastest measured (profiles/r01_experiments.md). */
+/* Selects the blind-rotate kernel.  0 = automatic (default): the persistent throughput kernel (one 64-thread block per
+ * gate-item, key rows by LDG straight from L2), except for small batches — at most two gates per SM on the 80/110/128-bit
+ * sets run kernel 9, at most one ciphertext per SM on the L <= 2 sets (Uint1-5 / programmable bootstraps) runs kernel 12.
+ * 9 = latency mode: four warps per gate, the two polynomials of a CMUX step in parallel (exact sets only).
+ * 10 = the throughput kernel at every batch size.  12 = latency mode that keeps the reference's accumulation order
+ * (bit-identical for every set).  All compute identical results.  Values 1-8, 11, 13 name the measured-slower round-1
+ * experiments (profiles/r01_experiments.md) and exist only in a library built with -DTFHE_EXPERIMENTAL=1. */
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
+/* The throughput kernel runs persistent blocks over WORK ITEMS of `steps` consecutive CMUX steps of one gate (the
+ * accumulator is handed from item to item through device memory), so that a batch that is not a multiple of the
+ * resident blocks still fills the SMs to the end.  0 = automatic (default: whole gates for batches that fit the
+ * resident blocks, ~n/14-step items above), >= n = whole gates.  Results do not depend on it. */
+int tfhe_ctx_set_blind_rotate_chunk_steps(tfhe_ctx* ctx, int steps);
 /* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default: the contraction wherever it exists), 1 = one block per
  * ciphertext gathering its N*t*(1-1/base) key rows out of L2, 2 = the whole batch as one exact u8 x u8 -> s32
  * contraction on the tensor cores (tcgen05.mma kind::i8 over the byte planes of the key; basebit = 2 parameter sets

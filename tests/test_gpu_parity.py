@@ -71,63 +71,61 @@ def test_blind_rotate_bit_exact(O, gpu, name):  # rows a7, a8, a15
 
 
 @pytest.mark.parametrize("name", ["80", "uint1", "uint2", "uint5"])
-def test_key_fetch_variants_agree(O, gpu, name):
-    """The three ways the kernel can read key rows (LDG from L2, TMA-staged shared memory, texture pipe) run the same
-    arithmetic in the same order: outputs are bit-identical to each other (and, at 80-bit, to the oracle)."""
+def test_kernel_variants_agree(T, O, gpu, name):
+    """Every blind-rotate kernel of the library gives the same words: the throughput kernel, the latency kernels the
+    engine picks for small batches, and (only in a -DTFHE_EXPERIMENTAL=1 build) the round-1 experiments."""
     P, sk, ck, ctx = gpu(name)
     ct = sk.encrypt_bool([0, 1, 1, 0, 1, 0, 0, 1], 5) if name == "80" else sk.encrypt_message([1, 0, 1], 2, 5)
     ct[1, 3] = ct[1, 4] = ct[2, 0] = 0  # mask words that round to X^0: the skipped-step paths (differ per gate of a shared block)
     outs = {}
+    names = ["throughput", "ldg"] + (["lat"] if name == "80" else ["latp"])
+    experimental = ["tma", "tex"] + (["lat2", "cl"] if name == "80" else []) + \
+                   (["w16", "tmex", "tmex+tma", "tms", "mg"] if P.N == 1024 else []) + (["tmem"] if P.N >= 1024 else [])
     try:
-        for v in ("throughput", "tma", "tex"):  # "throughput" = the default LDG kernel, never the small-batch latency kernel
+        for v in names:
             ctx.set_blind_rotate_variant(v)
-            outs["ldg" if v == "throughput" else v] = ctx.blind_rotate_batch(ct)
-        if name == "80":  # latency kernel (4 warps per gate, partial sums in a different order): exact sets only
-            ctx.set_blind_rotate_variant("lat")
-            outs["lat"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("lat2")  # one 64-thread group per digit
-            outs["lat2"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("cl")    # one cluster of 2L blocks per gate, partial products through DSMEM
-            outs["cl"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("ldg")  # default: picks a latency kernel by itself for this batch size
-            outs["auto"] = ctx.blind_rotate_batch(ct)
-        if name != "80":  # order-preserving latency kernel of the L <= 2 sets: bit-identical by construction
-            ctx.set_blind_rotate_variant("latp")
-            outs["latp"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("ldg")  # default: picks it by itself for this batch size
-            outs["autop"] = ctx.blind_rotate_batch(ct)
-        if P.N == 1024:  # warp-per-gate kernel with TMEM accumulators: a different transform schedule, same exact result
-            ctx.set_blind_rotate_variant("w16")
-            outs["w16"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("tmex")  # block per gate, second exchange through TMEM + lane shuffle
-            outs["tmex"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("tmex+tma")
-            outs["tmex+tma"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("tms")  # 6 blocks/SM: TMEM accumulators + TMA-staged key rows, 158 registers
-            outs["tms"] = ctx.blind_rotate_batch(ct)
-            ctx.set_blind_rotate_variant("mg")   # 6 gates per block sharing one staged copy of the key rows (8 gates: one full + one partial block)
-            outs["mg"] = ctx.blind_rotate_batch(ct)
-        if P.N >= 1024:
-            ctx.set_blind_rotate_variant("tmem")  # block-per-gate kernel with the accumulators in TMEM
-            outs["tmem"] = ctx.blind_rotate_batch(ct)
+            outs[v] = ctx.blind_rotate_batch(ct)
+        for v in experimental:
+            try:
+                ctx.set_blind_rotate_variant(v)
+            except T.TfheError as e:
+                assert "experimental" in str(e)
+                continue
+            outs[v] = ctx.blind_rotate_batch(ct)
     finally:
         ctx.set_blind_rotate_variant("ldg")
-    assert np.array_equal(outs["ldg"], outs["tma"]) and np.array_equal(outs["ldg"], outs["tex"])
-    if "w16" in outs:
-        assert np.array_equal(outs["ldg"], outs["w16"])
-        assert np.array_equal(outs["ldg"], outs["tmex"]) and np.array_equal(outs["ldg"], outs["tmex+tma"])
-        assert np.array_equal(outs["ldg"], outs["tms"]) and np.array_equal(outs["ldg"], outs["mg"])
-    if "tmem" in outs:
-        assert np.array_equal(outs["ldg"], outs["tmem"])
-    if "latp" in outs:
-        assert np.array_equal(outs["ldg"], outs["latp"]) and np.array_equal(outs["ldg"], outs["autop"])
-    if "lat" in outs:
-        assert np.array_equal(outs["ldg"], outs["lat"]) and np.array_equal(outs["ldg"], outs["auto"])
-        assert np.array_equal(outs["ldg"], outs["lat2"]) and np.array_equal(outs["ldg"], outs["cl"])
+    for v, o in outs.items():
+        assert np.array_equal(outs["throughput"], o), v
     if name == "80":
         ev = O.Evaluator(P.N)
         want = np.stack([ev.blind_rotate(P, c, ck.testvec, ck.bsk_fft, ck.offset) for c in ct])
-        assert np.array_equal(outs["ldg"].reshape(len(ct), -1), want)
+        assert np.array_equal(outs["throughput"].reshape(len(ct), -1), want)
+
+
+@pytest.mark.parametrize("name", ["80", "uint5"])
+def test_work_item_chunking_bit_identical(O, gpu, name):
+    """The persistent throughput kernel cuts a gate's n CMUX steps into work items and hands the accumulator from item
+    to item through device memory (blind_rotate.cuh).  Whatever the item size — whole gates, a few steps (items of one
+    gate then run on different SMs and really wait for each other), a size that does not divide n — the words are the
+    same, for the TRLWE output (hand-over through the output rows) and the extracted output (through scratch)."""
+    P, sk, ck, ctx = gpu(name)
+    cnt = 40
+    ct = sk.encrypt_bool(np.arange(cnt) % 2, 9) if name == "80" else sk.encrypt_message(np.arange(cnt) % 32, 32, 9)
+    ct[3, :8] = 0
+    try:
+        ctx.set_blind_rotate_variant("throughput")
+        ctx.set_blind_rotate_chunk_steps(P.n)
+        ref_rot, ref_bs = ctx.blind_rotate_batch(ct), ctx.bootstrap_batch(ct)
+        for steps in (1, 7, 53, P.n - 1, 0):
+            ctx.set_blind_rotate_chunk_steps(steps)
+            assert np.array_equal(ctx.blind_rotate_batch(ct), ref_rot), steps
+            assert np.array_equal(ctx.bootstrap_batch(ct), ref_bs), steps
+            assert np.array_equal(ctx.bootstrap_batch(ct), ref_bs), steps   # control words re-armed by the previous launch
+    finally:
+        ctx.set_blind_rotate_chunk_steps(0)
+        ctx.set_blind_rotate_variant("ldg")
+    if name == "80":
+        assert np.array_equal(ref_bs, O.bootstrap_batch(ck, ct))
 
 
 def test_sample_extract_and_key_switch_bit_exact(O, gpu):  # rows a16, a17
