@@ -63,7 +63,8 @@ def engine():
         lib.tfhe_circuit_run.argtypes = [vp, i64, i32, i32, vp, vp, i32, vp, vp]
         lib.tfhe_ctx_set_timing.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_set_blind_rotate_variant.argtypes = [vp, ctypes.c_int]
-        lib.tfhe_ctx_set_blind_rotate_chunk_steps.argtypes = [vp, ctypes.c_int]
+        if hasattr(lib, "tfhe_ctx_set_blind_rotate_chunk_steps"):  # absent from pre-round-2 builds used in A/B runs
+            lib.tfhe_ctx_set_blind_rotate_chunk_steps.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_set_key_switch_variant.argtypes = [vp, ctypes.c_int]
         lib.tfhe_ctx_generate_cloudkey.argtypes = [vp, vp, vp, ctypes.c_double, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, vp, vp, vp, vp]
         lib.tfhe_ctx_collect_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 4)]

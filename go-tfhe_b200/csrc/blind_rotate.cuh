@@ -44,7 +44,7 @@
 #define TFHE_BR_PAIR_FWD 0      // forward transforms of consecutive decomposition levels run interleaved in pairs
 #endif
 #ifndef TFHE_BR_PF_L1
-#define TFHE_BR_PF_L1 1         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread)
+#define TFHE_BR_PF_L1 0         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread).  +0.5 % with the round-1 kernel, -3.7 % with the persistent work-item kernel (97.1 k -> 100.7 k gates/s without it): off
 #endif
 #ifndef TFHE_BR_KO
 #define TFHE_BR_KO 0            // TIMING EXPERIMENTS ONLY (wrong results): bit 0 = no exchanges, bit 1 = no key loads, bit 2 = no barrier in exchanges
@@ -520,11 +520,22 @@ __device__ __forceinline__ uint32_t rot_read(const uint32_t* P, int idx) {
 // One CMUX step on the shared-memory accumulator: acc += BK (x) (X^at * acc - acc).
 // ---------------------------------------------------------------------------------------------
 // key-row fetch policies for the MAC: straight LDG (LSU pipe) or texture fetch (TEX pipe)
+#ifndef TFHE_BR_KEYLD
+#define TFHE_BR_KEYLD 0   // how key rows are loaded: 0 = ld.global.nc (L1-allocating; measured best), 1 = ld.global.cg (L2 only: -1.1 %), 2 = ld.global.nc.L1::no_allocate (same as 0)
+#endif
 struct KeyLdg {
   const double2* __restrict__ p;
   __device__ __forceinline__ double2 operator()(int idx) const {
     if (TFHE_BR_KO & 2) return make_double2(1e-9 * idx, 2e-9 * idx);
+#if TFHE_BR_KEYLD == 1
+    return __ldcg(p + idx);
+#elif TFHE_BR_KEYLD == 2
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+    return v;
+#else
     return __ldg(p + idx);
+#endif
   }
 };
 struct KeyTex {
