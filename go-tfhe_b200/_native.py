@@ -19,10 +19,10 @@ class TfheParams(ctypes.Structure):
 
 
 ENGINE_SYMBOLS = [
-    "tfhe_ctx_create", "tfhe_ctx_destroy", "tfhe_last_error", "tfhe_ctx_load_cloudkey",
+    "tfhe_ctx_create", "tfhe_ctx_create_multi", "tfhe_ctx_device_count", "tfhe_ctx_set_pipeline_chunk", "tfhe_ctx_destroy", "tfhe_last_error", "tfhe_ctx_load_cloudkey",
     "tfhe_ctx_load_cloudkey_device", "tfhe_bootstrap_batch", "tfhe_gate_batch", "tfhe_blind_rotate_batch",
     "tfhe_cmux_batch", "tfhe_sample_extract_batch", "tfhe_key_switch_batch", "tfhe_bootstrap_batch_device",
-    "tfhe_gate_batch_device", "tfhe_circuit_run", "tfhe_to_fourier_batch", "tfhe_to_poly_batch", "tfhe_mul_poly_batch", "tfhe_ctx_kernel_launches", "tfhe_ctx_set_timing", "tfhe_ctx_set_blind_rotate_variant", "tfhe_ctx_set_blind_rotate_chunk_steps", "tfhe_ctx_set_key_switch_variant", "tfhe_ctx_generate_cloudkey", "tfhe_ctx_collect_timing", "tfhe_ctx_algorithmic_bytes_per_bootstrap", "tfhe_version",
+    "tfhe_gate_batch_device", "tfhe_circuit_run", "tfhe_to_fourier_batch", "tfhe_to_poly_batch", "tfhe_mul_poly_batch", "tfhe_ctx_kernel_launches", "tfhe_ctx_set_timing", "tfhe_ctx_set_blind_rotate_variant", "tfhe_ctx_set_blind_rotate_chunk_steps", "tfhe_ctx_set_key_switch_variant", "tfhe_ctx_generate_cloudkey", "tfhe_ctx_collect_timing", "tfhe_ctx_algorithmic_bytes_per_bootstrap", "tfhe_fp64_peak_probe", "tfhe_version",
 ]
 CLIENT_SYMBOLS = [
     "tfhe_client_secret_key", "tfhe_client_encrypt_bool", "tfhe_client_decrypt_bool", "tfhe_client_encrypt_message",
@@ -43,6 +43,10 @@ def engine():
         lib = ctypes.CDLL(ENGINE_PATH)
         vp, i64, i32, u32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32
         lib.tfhe_ctx_create.argtypes = [ctypes.POINTER(TfheParams), ctypes.c_int, ctypes.POINTER(vp)]
+        if hasattr(lib, "tfhe_ctx_create_multi"):
+            lib.tfhe_ctx_create_multi.argtypes = [ctypes.POINTER(TfheParams), ctypes.c_int, vp, ctypes.POINTER(vp)]
+            lib.tfhe_ctx_device_count.argtypes = [vp]
+            lib.tfhe_ctx_set_pipeline_chunk.argtypes = [vp, i64]
         lib.tfhe_ctx_destroy.argtypes = [vp]
         lib.tfhe_ctx_destroy.restype = None
         lib.tfhe_last_error.argtypes = [vp]
@@ -72,6 +76,8 @@ def engine():
         lib.tfhe_ctx_kernel_launches.restype = i64
         lib.tfhe_ctx_algorithmic_bytes_per_bootstrap.argtypes = [vp]
         lib.tfhe_ctx_algorithmic_bytes_per_bootstrap.restype = i64
+        if hasattr(lib, "tfhe_fp64_peak_probe"):
+            lib.tfhe_fp64_peak_probe.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double * 3)]
         lib.tfhe_version.restype = ctypes.c_char_p
         _engine = lib
     return _engine

@@ -29,7 +29,7 @@
 #define TFHE_BR_UNROLL_LVL 1    // 1 = level loop rolled (measured best: smaller code, no spills), >= L = fully unrolled
 #endif
 #ifndef TFHE_BR_KEEP_OWN
-#define TFHE_BR_KEEP_OWN 0      // 1: exchanges keep the one point that does not change owner in its register (measured 3.5% slower: the predicated asm blocks pin the schedule)
+#define TFHE_BR_KEEP_OWN 0      // exchanges keep the one point that does not change owner in its register: 1 = in every exchange between full passes (round 1: 3.5 % slower), 2 = only where the kept slot is the same for 8 consecutive lanes, i.e. where a whole quarter-warp wavefront disappears
 #endif
 #ifndef TFHE_BR_TL_RELOAD
 #define TFHE_BR_TL_RELOAD 0     // 1: last-pass twiddles re-read from L1 every transform (frees 16 registers)
@@ -234,6 +234,21 @@ __device__ __forceinline__ void lds_if(double2& v, const double2* p, bool pred) 
       : "memory");
 }
 
+// predicated on (own != A) with the comparison inside the asm block: one ISETP + one predicated LDS/STS
+template <int A>
+__device__ __forceinline__ void lds_unless(double2& v, const double2* p, int own) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, %4;\n\t@q ld.shared.v2.f64 {%0, %1}, [%2];\n\t}"
+               : "+d"(v.x), "+d"(v.y)
+               : "r"(smem_u32(p)), "r"(own), "n"(A)
+               : "memory");
+}
+template <int A>
+__device__ __forceinline__ void sts_unless(double2* p, const double2& v, int own) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, %4;\n\t@q st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(smem_u32(p)),
+               "d"(v.x), "d"(v.y), "r"(own), "n"(A)
+               : "memory");
+}
+
 __device__ __forceinline__ void sts_if(double2* p, const double2& v, bool pred) {
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.shared.v2.f64 [%0], {%1, %2};\n\t}" ::"r"(smem_u32(p)),
                "d"(v.x), "d"(v.y), "r"((int)pred)
@@ -304,20 +319,31 @@ struct Fft {
     const int wb = G::base(KW, tau), rb = G::base(KR, tau);
     // Between two full passes exactly one of a thread's 8 points keeps both its owner and its register slot
     // (slot (tau / finer stride) % 8): it stays in its register, skipping 1/8 of the shared-memory traffic.
-    constexpr bool KEEP = TFHE_BR_KEEP_OWN && (KW < G::NFULL) && (KR < G::NFULL);
+    // (mode 2: only if that slot is uniform over 8 consecutive lanes — the finer pass's stride is a multiple of 8 — so that
+    // the skipped accesses of a 16-byte instruction form a whole quarter-warp, i.e. one of its four 128-byte wavefronts)
+    constexpr bool KEEP = TFHE_BR_KEEP_OWN && (KW < G::NFULL) && (KR < G::NFULL) &&
+                          (TFHE_BR_KEEP_OWN == 1 || G::stride(KW > KR ? KW : KR) % 8 == 0);
     const int own = KEEP ? ((tau / G::stride(KW > KR ? KW : KR)) & 7) : -1;
+    if constexpr (KEEP) {
+      sts_unless<0>(buf + swz(wb + G::stride(KW) * 0), x[0], own); sts_unless<1>(buf + swz(wb + G::stride(KW) * 1), x[1], own);
+      sts_unless<2>(buf + swz(wb + G::stride(KW) * 2), x[2], own); sts_unless<3>(buf + swz(wb + G::stride(KW) * 3), x[3], own);
+      sts_unless<4>(buf + swz(wb + G::stride(KW) * 4), x[4], own); sts_unless<5>(buf + swz(wb + G::stride(KW) * 5), x[5], own);
+      sts_unless<6>(buf + swz(wb + G::stride(KW) * 6), x[6], own); sts_unless<7>(buf + swz(wb + G::stride(KW) * 7), x[7], own);
+    } else {
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      if constexpr (KEEP) sts_if(buf + swz(wb + G::stride(KW) * a), x[a], a != own);
-      else buf[swz(wb + G::stride(KW) * a)] = x[a];
+      for (int a = 0; a < 8; a++) buf[swz(wb + G::stride(KW) * a)] = x[a];
     }
     if constexpr (WARP_LOCAL) __syncwarp();
     else if (!(TFHE_BR_KO & 4)) group_barrier();
     hook();
+    if constexpr (KEEP) {  // predicated, never a branch
+      lds_unless<0>(x[0], buf + swz(rb + G::stride(KR) * 0), own); lds_unless<1>(x[1], buf + swz(rb + G::stride(KR) * 1), own);
+      lds_unless<2>(x[2], buf + swz(rb + G::stride(KR) * 2), own); lds_unless<3>(x[3], buf + swz(rb + G::stride(KR) * 3), own);
+      lds_unless<4>(x[4], buf + swz(rb + G::stride(KR) * 4), own); lds_unless<5>(x[5], buf + swz(rb + G::stride(KR) * 5), own);
+      lds_unless<6>(x[6], buf + swz(rb + G::stride(KR) * 6), own); lds_unless<7>(x[7], buf + swz(rb + G::stride(KR) * 7), own);
+    } else {
 #pragma unroll
-    for (int a = 0; a < 8; a++) {
-      if constexpr (KEEP) lds_if(x[a], buf + swz(rb + G::stride(KR) * a), a != own);  // predicated, never a branch
-      else x[a] = buf[swz(rb + G::stride(KR) * a)];
+      for (int a = 0; a < 8; a++) x[a] = buf[swz(rb + G::stride(KR) * a)];
     }
     if constexpr (SINGLE) mbar_arrive(rd_bar);
   }
@@ -520,6 +546,24 @@ __device__ __forceinline__ uint32_t rot_read(const uint32_t* P, int idx) {
 // One CMUX step on the shared-memory accumulator: acc += BK (x) (X^at * acc - acc).
 // ---------------------------------------------------------------------------------------------
 // key-row fetch policies for the MAC: straight LDG (LSU pipe) or texture fetch (TEX pipe)
+// Device layout of one bootstrapping-key row-set (2L rows x {A,B} x M spectrum values, double2 units).
+// TFHE_BR_KEY256 = 0 (default): [row][{A,B}][e][tau] — every warp-wide 16-byte load covers 512 contiguous bytes.
+// TFHE_BR_KEY256 = 1: the A and the B value a thread multiplies one spectrum point with are adjacent (32 bytes), so a
+// multiply-accumulate fetches them with ONE 256-bit load (LDG.E.ENL2.256): half the load instructions for the same
+// bytes.  Measured (profiles/r02_experiments.md): no gain for the throughput kernel (its time follows LSU wavefronts, not
+// instructions) and the latency kernels' 16-byte cp.async pieces then use half of every 32-byte sector (single gate
+// 2.5 -> 3.7 ms), so it stays off.
+#ifndef TFHE_BR_KEY256
+#define TFHE_BR_KEY256 0
+#endif
+template <int T>
+__host__ __device__ constexpr int key_pos(int r, int ab, int e, int tau) {
+#if TFHE_BR_KEY256
+  return ((r * 8 + e) * T + tau) * 2 + ab;
+#else
+  return ((r * 2 + ab) * 8 + e) * T + tau;
+#endif
+}
 #ifndef TFHE_BR_KEYLD
 #define TFHE_BR_KEYLD 0   // how key rows are loaded: 0 = ld.global.nc (L1-allocating; measured best), 1 = ld.global.cg (L2 only: -1.1 %), 2 = ld.global.nc.L1::no_allocate (same as 0)
 #endif
@@ -537,6 +581,19 @@ struct KeyLdg {
     return __ldg(p + idx);
 #endif
   }
+  // the two key values (A row, B row) for spectrum slot e of row r
+  template <int T>
+  __device__ __forceinline__ void pair(int r, int e, int tau, double2& ka, double2& kb) const {
+#if TFHE_BR_KEY256
+    if (TFHE_BR_KO & 2) { ka = make_double2(1e-9 * e, 2e-9 * r); kb = ka; return; }
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+                 : "=d"(ka.x), "=d"(ka.y), "=d"(kb.x), "=d"(kb.y)
+                 : "l"(p + key_pos<T>(r, 0, e, tau)));
+#else
+    ka = (*this)(key_pos<T>(r, 0, e, tau));
+    kb = (*this)(key_pos<T>(r, 1, e, tau));
+#endif
+  }
 };
 struct KeyTex {
   cudaTextureObject_t tex;
@@ -544,6 +601,11 @@ struct KeyTex {
   __device__ __forceinline__ double2 operator()(int idx) const {
     const uint4 v = tex1Dfetch<uint4>(tex, base + idx);
     return make_double2(__hiloint2double((int)v.y, (int)v.x), __hiloint2double((int)v.w, (int)v.z));
+  }
+  template <int T>
+  __device__ __forceinline__ void pair(int r, int e, int tau, double2& ka, double2& kb) const {
+    ka = (*this)(key_pos<T>(r, 0, e, tau));
+    kb = (*this)(key_pos<T>(r, 1, e, tau));
   }
 };
 
@@ -575,8 +637,6 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
 
   // spectrum of one digit polynomial times key row r, accumulated into both output spectra
   auto mac = [&](const double2 (&x)[8], int r) {
-    const int rowA = (r * 2 + 0) * M + tau;
-    const int rowB = rowA + M;
 #if TFHE_BR_PF_L1
     if constexpr (!std::is_same<Key, KeyTex>::value) {  // rows of digit r + d (contiguous into the next step's row-set)
       const char* pf = reinterpret_cast<const char*>(bk.p + (r + TFHE_BR_PF_L1) * 2 * M) + tau * 128;
@@ -586,7 +646,8 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
 #endif
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const double2 ka = bk(rowA + e * T), kb = bk(rowB + e * T);
+      double2 ka, kb;
+      bk.template pair<T>(r, e, tau, ka, kb);
       accA[e].x = fma(x[e].x, ka.x, accA[e].x);
       accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
       accA[e].y = fma(x[e].x, ka.y, accA[e].y);
@@ -711,6 +772,9 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
   Fft<LOGN - 1> fft;
   fft.init(ex, A.tw_tab, tau);
   const size_t row_stride = (size_t)2 * L * 2 * M;
+#ifdef TFHE_BR_STAGGER  // experiment: start the co-resident blocks of an SM a fraction of a step apart
+  __nanosleep((blockIdx.x / 148u) * TFHE_BR_STAGGER);
+#endif
 
   for (;;) {
     if (tau == 0) s_item = atomicAdd(&A.ctl[0], 1u);
@@ -1042,7 +1106,6 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const Cmu
   fft.init(ex, A.tw_tab, tau);
   __syncthreads();
   // Same data path as cmux_rotate_step but the second operand comes from c1 instead of a rotation.
-  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
   double2 accA[8], accB[8];
 #pragma unroll
   for (int e = 0; e < 8; e++) { accA[e] = make_double2(0.0, 0.0); accB[e] = make_double2(0.0, 0.0); }
@@ -1058,7 +1121,6 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const Cmu
 #pragma unroll
     for (int lvl = 0; lvl < L; lvl++) {
       double2 x[8];
-      constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
       const int sh = 32 - (lvl + 1) * BGBIT;
 #pragma unroll
       for (int a = 0; a < 8; a++) {
@@ -1066,12 +1128,10 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), MINB) cmux_kernel(const Cmu
         x[a].y = digit_scaled<BGBIT>(dim[a], sh);
       }
       fft.forward(x, A.tw0);
-      const double2* __restrict__ rowA = A.bsk_row + ((poly * L + lvl) * 2 + 0) * M + tau;
-      const double2* __restrict__ rowB = rowA + M;
 #pragma unroll
       for (int e = 0; e < 8; e++) {
-        const double2 ka = __ldg(rowA + e * T);
-        const double2 kb = __ldg(rowB + e * T);
+        const double2 ka = __ldg(A.bsk_row + key_pos<T>(poly * L + lvl, 0, e, tau));
+        const double2 kb = __ldg(A.bsk_row + key_pos<T>(poly * L + lvl, 1, e, tau));
         accA[e].x = fma(x[e].x, ka.x, accA[e].x);
         accA[e].x = fma(-x[e].y, ka.y, accA[e].x);
         accA[e].y = fma(x[e].x, ka.y, accA[e].y);

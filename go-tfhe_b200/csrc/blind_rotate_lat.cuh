@@ -31,8 +31,6 @@ template <int LOGN, int L, int BGBIT, bool SMALL>
 __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_kernel(const BrArgs A) {
   static_assert(SMALL, "partial sums are reordered: exact parameter sets only");
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
-  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
-  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                              // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);                         // [2 groups][2][M]
@@ -47,11 +45,13 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
   // slots that only this thread reads, one digit ahead: with a single gate on the SM nothing else hides the L2 latency
   // of the key rows, and no registers are held in flight.  Thread-private slots need no barrier, only wait_group.
   double2* my_stage = stage + (size_t)grp * 16 * T + tau;
-  auto stage_keys = [&](const double2* rowA) {  // rowA already offset by tau; the B row follows M elements later
+  auto stage_keys = [&](const double2* rowset, int r) {  // row r of the row-set (r >= 2L runs into the next step's row-set)
+    const double2* base = rowset + (size_t)(r / (2 * L)) * (2 * L * 2 * M);
+    r %= 2 * L;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + e * T)), "l"(rowA + e * T) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (8 + e) * T)), "l"(rowA + M + e * T) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + e * T)), "l"(base + key_pos<T>(r, 0, e, tau)) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (8 + e) * T)), "l"(base + key_pos<T>(r, 1, e, tau)) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -77,10 +77,10 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
   for (int i = 0; i < n; i++) {
     const int at = abar[i];
     if (at == 0) continue;  // uniform over the block
-    const double2* __restrict__ bk = A.bsk + row_stride * i + tau;
+    const double2* __restrict__ bk = A.bsk + row_stride * i;
     if (staged != i) {  // first step, or the one after a skipped step: drop whatever is in flight, then stage the right rows
       asm volatile("cp.async.wait_group 0;" ::: "memory");
-      stage_keys(bk + (size_t)(grp * L * 2) * M);
+      stage_keys(bk, grp * L);
     }
     double2 accA[8], accB[8];
 #pragma unroll
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
       for (int e = 0; e < 8; e++) { ka[e] = my_stage[e * T]; kb[e] = my_stage[(8 + e) * T]; }
       // next digit of this group: next level, or the first level of the next step (row-sets are contiguous; the key
       // buffer has slack past the last step) — its L2 latency hides behind the next transform(s)
-      stage_keys(bk + ((lvl + 1 < L) ? (size_t)((grp * L + lvl + 1) * 2) * M : row_stride + (size_t)(grp * L * 2) * M));
+      stage_keys(bk, (lvl + 1 < L) ? grp * L + lvl + 1 : 2 * L + grp * L);
 #pragma unroll
       for (int e = 0; e < 8; e++) {
         accA[e].x = fma(x[e].x, ka[e].x, accA[e].x);
@@ -182,8 +182,6 @@ template <int LOGN, int L, int BGBIT, bool SMALL>
 __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_latp_kernel(const BrArgs A) {
   static_assert(L <= 2, "group 1 keeps its L digit spectra in registers");
   constexpr int N = 1 << LOGN, M = N / 2, T = M / 8;
-  constexpr uint32_t MASK = (BGBIT == 32) ? 0xFFFFFFFFu : ((1u << BGBIT) - 1u);
-  constexpr double BIAS = 4503599627370496.0 + (double)(1u << (BGBIT - 1));
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint32_t* acc = reinterpret_cast<uint32_t*>(smem_raw);                                // [2][N]
   double2* ex = reinterpret_cast<double2*>(smem_raw + 8 * N);                           // [2 groups][2][M]
@@ -232,15 +230,15 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_latp_ke
     const int at = abar[i];
     if (at == 0) continue;  // uniform over the block
     {  // this group's L x 16 key values of this step, asynchronously into thread-private slots (hidden behind the transforms)
-      const double2* __restrict__ rows = A.bsk + row_stride * i + (size_t)(grp * L * 2) * M + tau;
+      const double2* __restrict__ rows = A.bsk + row_stride * i;
 #pragma unroll
       for (int l = 0; l < L; l++)
 #pragma unroll
         for (int e = 0; e < 8; e++) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (size_t)(l * 16 + e) * T)),
-                       "l"(rows + (size_t)(l * 2) * M + e * T) : "memory");
+                       "l"(rows + key_pos<T>(grp * L + l, 0, e, tau)) : "memory");
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(my_stage + (size_t)(l * 16 + 8 + e) * T)),
-                       "l"(rows + (size_t)(l * 2 + 1) * M + e * T) : "memory");
+                       "l"(rows + key_pos<T>(grp * L + l, 1, e, tau)) : "memory");
         }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }

@@ -32,30 +32,39 @@ __device__ __forceinline__ void gate_coeffs(int op, uint32_t& sa, uint32_t& sb, 
   }
 }
 
-// grid.x = count, block = 256.  ops: [nops] with nops in {1,count}.  For MUX gates (op 10) the
-// first-level jobs are AND(a,b) -> out0[g] and ANDNY(a,c) -> out1[g]  (AND(NOT a, c) == ANDNY(a,c)
-// word for word: (0 - a) + c - 1/8).  Non-MUX gates write their prepared ciphertext to out0[g] and
-// leave out1[g] untouched.  NOT / COPY write their final result to out0 as well (no bootstrap).
-__global__ void gate_prepare_kernel(long long count, const uint8_t* __restrict__ ops, long long nops,
+// grid.x = count, block = 256.  op_uniform >= 0: every gate has that opcode; else ops[g].  A gate that bootstraps
+// writes its prepared ciphertext(s) into the compacted JOB batch `jobs`: job = job_of ? job_of[g] : g;
+//   two-input gate  ->  jobs[job]                                   (job in [0, nb))
+//   MUX (op 10)     ->  AND(a,b) at jobs[nb + job], ANDNY(a,c) at jobs[nb + nm + job]   (job in [0, nm);
+//                       AND(NOT a, c) == ANDNY(a,c) word for word: (0 - a) + c - 1/8)
+// NOT / COPY (no bootstrap) write their final result to direct_out[g].
+__global__ void gate_prepare_kernel(long long count, const uint8_t* __restrict__ ops, int op_uniform,
                                     const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
-                                    const uint32_t* __restrict__ c, uint32_t* __restrict__ out0,
-                                    uint32_t* __restrict__ out1, int n) {
+                                    const uint32_t* __restrict__ c, const int* __restrict__ job_of,
+                                    uint32_t* __restrict__ jobs, long long nb, long long nm,
+                                    uint32_t* __restrict__ direct_out, int n) {
   const long long g = blockIdx.x;
-  const int op = ops[nops == 1 ? 0 : g];
+  const int op = op_uniform >= 0 ? op_uniform : ops[g];
   const size_t row = (size_t)g * (n + 1);
+  const long long job = job_of ? job_of[g] : g;
   uint32_t sa, sb, bias;
   if (op == 10) {
+    uint32_t* o0 = jobs + (size_t)(nb + job) * (n + 1);
+    uint32_t* o1 = jobs + (size_t)(nb + nm + job) * (n + 1);
     gate_coeffs(1, sa, sb, bias);
     for (int i = threadIdx.x; i <= n; i += blockDim.x)
-      out0[row + i] = sa * a[row + i] + sb * b[row + i] + (i == n ? bias : 0u);
+      o0[i] = sa * a[row + i] + sb * b[row + i] + (i == n ? bias : 0u);
     gate_coeffs(6, sa, sb, bias);
     for (int i = threadIdx.x; i <= n; i += blockDim.x)
-      out1[row + i] = sa * a[row + i] + sb * c[row + i] + (i == n ? bias : 0u);
+      o1[i] = sa * a[row + i] + sb * c[row + i] + (i == n ? bias : 0u);
+  } else if (op >= 11) {
+    gate_coeffs(op, sa, sb, bias);
+    for (int i = threadIdx.x; i <= n; i += blockDim.x) direct_out[row + i] = sa * a[row + i];
   } else {
     gate_coeffs(op, sa, sb, bias);
-    const bool unary = (op >= 11);
+    uint32_t* o = jobs + (size_t)job * (n + 1);
     for (int i = threadIdx.x; i <= n; i += blockDim.x)
-      out0[row + i] = sa * a[row + i] + (unary ? 0u : sb * b[row + i]) + (i == n ? bias : 0u);
+      o[i] = sa * a[row + i] + sb * b[row + i] + (i == n ? bias : 0u);
   }
 }
 
@@ -226,7 +235,14 @@ __global__ void bsk_repack_kernel(const double* __restrict__ src, double2* __res
     const double re = src[poly * N + (k >> 2) * 8 + (k & 3)];
     const double im = src[poly * N + (k >> 2) * 8 + 4 + (k & 3)];
     const int tau = k >> 3, e = k & 7;
-    dst[poly * M + e * T + tau] = make_double2(re * scale, im * scale);
+    const size_t rowset = poly / (size_t)(4 * L);                 // CMUX step
+    const int r = (int)((poly / 2) % (size_t)(2 * L)), ab = (int)(poly & 1);
+#if TFHE_BR_KEY256
+    const size_t pos = ((size_t)(r * 8 + e) * T + tau) * 2 + ab;  // key_pos (blind_rotate.cuh): A and B values adjacent
+#else
+    const size_t pos = ((size_t)(r * 2 + ab) * 8 + e) * T + tau;
+#endif
+    dst[rowset * (size_t)(4 * L) * M + pos] = make_double2(re * scale, im * scale);
   }
 }
 

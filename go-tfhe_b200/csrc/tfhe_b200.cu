@@ -14,6 +14,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 // TFHE_EXPERIMENTAL: also builds the measured-slower blind-rotate variants of round 1 (TMA-staged / texture key fetch,
@@ -34,6 +35,7 @@
 #include "lwe_kernels.cuh"
 #include "key_switch_mma.cuh"
 #include "keygen.cuh"
+#include "fp64_probe.cuh"
 
 using namespace tfhe;
 
@@ -60,10 +62,22 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// staging slot of the pipelined host-buffer API: device copies of one chunk's inputs / outputs, the events that order
+// the three streams, and a pinned host buffer for the index lists of a mixed gate batch
+struct Slot {
+  DevBuf a, b, c, luts, out;
+  cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr, idx_done = nullptr;
+  int* h_idx = nullptr;
+  size_t h_idx_cap = 0;
+  bool idx_pending = false;
+};
+
 }  // namespace
 
 struct tfhe_ctx {
   tfhe_params P{};
+  // a context created by tfhe_ctx_create_multi owns one single-device context per GPU and no device state of its own
+  std::vector<tfhe_ctx*> kids;
   int device = 0;
   int logN = 0;
   int variant = -1;          // index into the kernel instantiation table
@@ -81,7 +95,10 @@ struct tfhe_ctx {
   int ks_variant = 0;              // 0 = auto, 1 = row gather (key_switch_kernel), 2 = tensor-core contraction
   DevBuf ks_sel;                   // selection matrix of the current chunk
   Tw4 tw0{};
-  cudaStream_t stream = nullptr;  // used by the host-buffer API
+  cudaStream_t stream = nullptr;  // used by the host-buffer API (compute)
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy-in / copy-out streams of the pipelined host-buffer calls
+  Slot slot[2];
+  int64_t pipe_chunk = 16384;     // ciphertexts per pipeline chunk
   DevBuf prep, lwe1, tmp, prep2, idx_a, idx_b, ops_dev;       // engine scratch
   DevBuf wires, gate_descs;                                   // circuit runner
   DevBuf h2d_a, h2d_b, h2d_c, h2d_luts, d2h_out;              // staging for the host-buffer API
@@ -517,6 +534,45 @@ int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32
   return 0;
 }
 
+bool is_group(const tfhe_ctx* c) { return !c->kids.empty(); }
+
+// --- multi-device groups ------------------------------------------------------------------------------------------
+// Contiguous shards of [0, count) over the kids of a group, cut where the running COST (bootstraps) is closest to an even
+// split; cost == nullptr: equal counts.
+std::vector<int64_t> shard_bounds(int ndev, int64_t count, const uint8_t* ops, int64_t nops) {
+  std::vector<int64_t> b(ndev + 1, 0);
+  if (!ops || nops == 1) {
+    for (int d = 0; d <= ndev; d++) b[d] = count * d / ndev;
+    return b;
+  }
+  auto cost = [](uint8_t op) -> int64_t { return op == TFHE_OP_MUX ? 3 : (op >= TFHE_OP_NOT ? 0 : 1); };
+  int64_t total = 0;
+  for (int64_t g = 0; g < count; g++) total += cost(ops[g]);
+  int64_t run = 0, g = 0;
+  for (int d = 1; d < ndev; d++) {
+    const int64_t want = total * d / ndev;
+    while (g < count && run + cost(ops[g]) <= want) run += cost(ops[g++]);
+    b[d] = g;
+  }
+  b[ndev] = count;
+  return b;
+}
+
+// runs fn(kid index) for every kid, kid 0 on the calling thread; returns the first failure and copies its message
+template <class Fn>
+int for_each_kid(tfhe_ctx* c, Fn fn) {
+  const int nd = (int)c->kids.size();
+  std::vector<int> rc(nd, 0);
+  std::vector<std::thread> th;
+  for (int d = 1; d < nd; d++) th.emplace_back([&, d] { rc[d] = fn(d); });
+  rc[0] = fn(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < nd; d++)
+    if (rc[d]) { c->err = "device " + std::to_string(c->kids[d]->device) + ": " + c->kids[d]->err; return rc[d]; }
+  return TFHE_OK;
+}
+
+
 int check_ready(tfhe_ctx* c, bool need_ksk) {
   if (!c) return TFHE_ERR_ARG;
   if (!c->key_loaded) return fail(c, TFHE_ERR_STATE, "cloud key not loaded");
@@ -590,6 +646,12 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   };
   if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+  for (Slot& sl : c->slot)
+    for (cudaEvent_t* ev : {&sl.in_done, &sl.comp_done, &sl.out_done, &sl.idx_done})
+      if ((e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+  if (const char* pc = getenv("TFHE_B200_PIPE_CHUNK")) c->pipe_chunk = std::max<int64_t>(256, atoll(pc));
   std::vector<Tw4> tab;
   switch (c->logN) {
     case 9: build_twiddles<8>(c->tw0, tab); break;
@@ -674,10 +736,57 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
   return TFHE_OK;
 }
 
+// One context over several GPUs of this process: the batch entry points with host buffers (tfhe_gate_batch,
+// tfhe_bootstrap_batch, tfhe_blind_rotate_batch, tfhe_circuit_run) shard their batch over the devices — what
+// trgsw.BatchBlindRotate's goroutine fan-out (trgsw/trgsw.go:234-252) becomes on a multi-GPU node.
+int tfhe_ctx_create_multi(const tfhe_params* params, int ndev, const int* devices, tfhe_ctx** out) {
+  if (!params || !out) return fail(nullptr, TFHE_ERR_ARG, "null argument");
+  *out = nullptr;
+  int visible = 0;
+  cudaError_t e = cudaGetDeviceCount(&visible);
+  if (e != cudaSuccess || visible == 0)
+    return fail(nullptr, TFHE_ERR_CUDA, "no CUDA device (%s); this engine has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (ndev <= 0) { ndev = visible; devices = nullptr; }
+  if (ndev > visible && !devices) return fail(nullptr, TFHE_ERR_ARG, "%d devices requested, %d visible", ndev, visible);
+  tfhe_ctx* g = new (std::nothrow) tfhe_ctx();
+  if (!g) return fail(nullptr, TFHE_ERR_NOMEM, "out of host memory");
+  g->P = *params;
+  for (int d = 0; d < ndev; d++) {
+    const int dev = devices ? devices[d] : d;
+    for (tfhe_ctx* k : g->kids)
+      if (k->device == dev) { tfhe_ctx_destroy(g); return fail(nullptr, TFHE_ERR_ARG, "device %d listed twice", dev); }
+    tfhe_ctx* k = nullptr;
+    const int rc = tfhe_ctx_create(params, dev, &k);
+    if (rc) {
+      if (g->kids.empty()) delete g; else tfhe_ctx_destroy(g);
+      return rc;  // message already recorded by tfhe_ctx_create
+    }
+    g->kids.push_back(k);
+  }
+  g->device = g->kids[0]->device; g->variant = g->kids[0]->variant; g->logN = g->kids[0]->logN; g->sm_count = g->kids[0]->sm_count;
+  *out = g;
+  return TFHE_OK;
+}
+
+int tfhe_ctx_device_count(const tfhe_ctx* c) { return c ? (is_group(c) ? (int)c->kids.size() : 1) : 0; }
+
 void tfhe_ctx_destroy(tfhe_ctx* c) {
   if (!c) return;
+  if (is_group(c)) {
+    for (tfhe_ctx* k : c->kids) tfhe_ctx_destroy(k);
+    delete c;
+    return;
+  }
   cudaSetDevice(c->device);
-  if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  for (cudaStream_t* st : {&c->stream, &c->s_in, &c->s_out})
+    if (*st) { cudaStreamSynchronize(*st); cudaStreamDestroy(*st); }
+  for (Slot& sl : c->slot) {
+    for (DevBuf* b : {&sl.a, &sl.b, &sl.c, &sl.luts, &sl.out}) b->release();
+    for (cudaEvent_t ev : {sl.in_done, sl.comp_done, sl.out_done, sl.idx_done})
+      if (ev) cudaEventDestroy(ev);
+    if (sl.h_idx) cudaFreeHost(sl.h_idx);
+  }
   for (DevBuf* b : {&c->wires, &c->gate_descs, &c->prep, &c->lwe1, &c->tmp, &c->prep2, &c->idx_a, &c->idx_b, &c->ops_dev, &c->h2d_a, &c->h2d_b,
                     &c->h2d_c, &c->h2d_luts, &c->d2h_out, &c->br_ctl, &c->br_scratch})
     b->release();
@@ -700,6 +809,7 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
 int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_bsk_fft, const uint32_t* d_ksk,
                                   const uint32_t* d_testvec, void* stream) {
   if (!c || !d_bsk_fft || !d_testvec) return fail(c, TFHE_ERR_ARG, "null argument");
+  if (is_group(c)) return fail(c, TFHE_ERR_ARG, "device-buffer entry points need a single-device context");
   int rc = set_device(c);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -763,9 +873,51 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
   return TFHE_OK;
 }
 
-int tfhe_ctx_load_cloudkey(tfhe_ctx* c, uint32_t offset, const double* bsk_fft, const uint32_t* ksk,
+}  // extern "C"
+
+namespace {
+// Replicates a cloud key that sits in reference layout in device 0's staging buffers to every other device of a group:
+// one peer copy per buffer (NVLink / NVSwitch when peer access exists, the driver's fallback otherwise), then the
+// ordinary repack on each device.  This is the "one broadcast of the cloud key at init" of the multi-GPU design; nothing
+// crosses devices afterwards.
+int group_replicate(tfhe_ctx* g, uint32_t offset, const void* d_bsk, size_t bsk_bytes, const void* d_ksk, size_t ksk_bytes,
+                    const void* d_tv, size_t tv_bytes) {
+  const int dev0 = g->kids[0]->device;
+  int rc = for_each_kid(g, [&](int d) -> int {
+    if (d == 0) return 0;
+    tfhe_ctx* k = g->kids[d];
+    int r = set_device(k);
+    if (r) return r;
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, k->device, dev0) == cudaSuccess && can) {
+      cudaError_t pe = cudaDeviceEnablePeerAccess(dev0, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+      else cudaGetLastError();
+    }
+    DevBuf b2, k2, t2;
+    cudaError_t e = b2.reserve(bsk_bytes);
+    if (e == cudaSuccess && d_ksk) e = k2.reserve(ksk_bytes);
+    if (e == cudaSuccess) e = t2.reserve(tv_bytes);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(b2.p, k->device, d_bsk, dev0, bsk_bytes, k->stream);
+    if (e == cudaSuccess && d_ksk) e = cudaMemcpyPeerAsync(k2.p, k->device, d_ksk, dev0, ksk_bytes, k->stream);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(t2.p, k->device, d_tv, dev0, tv_bytes, k->stream);
+    if (e == cudaSuccess)
+      r = tfhe_ctx_load_cloudkey_device(k, offset, b2.as<double>(), d_ksk ? k2.as<uint32_t>() : nullptr, t2.as<uint32_t>(), k->stream);
+    b2.release(); k2.release(); t2.release();
+    if (e != cudaSuccess) return fail(k, TFHE_ERR_CUDA, "peer copy of the cloud key: %s", cudaGetErrorString(e));
+    return r;
+  });
+  if (rc == 0) { g->key_loaded = true; g->has_ksk = d_ksk != nullptr; g->offset = offset; }
+  return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int tfhe_ctx_load_cloudkey(tfhe_ctx* g, uint32_t offset, const double* bsk_fft, const uint32_t* ksk,
                            const uint32_t* testvec) {
-  if (!c || !bsk_fft || !testvec) return fail(c, TFHE_ERR_ARG, "null argument");
+  if (!g || !bsk_fft || !testvec) return fail(g, TFHE_ERR_ARG, "null argument");
+  tfhe_ctx* c = is_group(g) ? g->kids[0] : g;
   int rc = set_device(c);
   if (rc) return rc;
   const tfhe_params& P = c->P;
@@ -781,18 +933,23 @@ int tfhe_ctx_load_cloudkey(tfhe_ctx* c, uint32_t offset, const double* bsk_fft, 
   if (e == cudaSuccess)
     rc = tfhe_ctx_load_cloudkey_device(c, offset, sb.as<double>(), ksk ? sk.as<uint32_t>() : nullptr, st.as<uint32_t>(),
                                        c->stream);
+  if (e == cudaSuccess && rc == 0 && is_group(g))
+    rc = group_replicate(g, offset, sb.p, bsk_bytes, ksk ? sk.p : nullptr, ksk_bytes, st.p, tv_bytes);
+  set_device(c);
   sb.release(); sk.release(); st.release();
-  if (e != cudaSuccess) return fail(c, TFHE_ERR_CUDA, "key upload: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(g, TFHE_ERR_CUDA, "key upload: %s", cudaGetErrorString(e));
+  if (rc && is_group(g) && g->err.empty()) g->err = c->err;
   return rc;
 }
 
 // cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-145) on the device; see keygen.cuh.
-int tfhe_ctx_generate_cloudkey(tfhe_ctx* c, const uint32_t* key_lv0, const uint32_t* key_lv1, double alpha_lv0,
+int tfhe_ctx_generate_cloudkey(tfhe_ctx* g, const uint32_t* key_lv0, const uint32_t* key_lv1, double alpha_lv0,
                                double alpha_lv1, uint64_t seed, int with_ksk, uint32_t* offset_out, double* bsk_fft_out,
                                uint32_t* ksk_out, uint32_t* testvec_out) {
-  if (!c || !key_lv0 || !key_lv1) return fail(c, TFHE_ERR_ARG, "null argument");
-  if (!(alpha_lv0 >= 0.0) || !(alpha_lv1 >= 0.0)) return fail(c, TFHE_ERR_ARG, "noise parameters must be >= 0");
-  if (ksk_out && !with_ksk) return fail(c, TFHE_ERR_ARG, "ksk_out given but with_ksk = 0");
+  if (!g || !key_lv0 || !key_lv1) return fail(g, TFHE_ERR_ARG, "null argument");
+  if (!(alpha_lv0 >= 0.0) || !(alpha_lv1 >= 0.0)) return fail(g, TFHE_ERR_ARG, "noise parameters must be >= 0");
+  if (ksk_out && !with_ksk) return fail(g, TFHE_ERR_ARG, "ksk_out given but with_ksk = 0");
+  tfhe_ctx* c = is_group(g) ? g->kids[0] : g;  // a group generates on its first device and replicates by peer copy
   int rc = set_device(c);
   if (rc) return rc;
   const tfhe_params& P = c->P;
@@ -845,8 +1002,12 @@ int tfhe_ctx_generate_cloudkey(tfhe_ctx* c, const uint32_t* key_lv0, const uint3
     if (e == cudaSuccess && testvec_out) memcpy(testvec_out, tv.data(), tv_bytes);
   }
   cudaStreamSynchronize(s);
+  if (e == cudaSuccess && rc == 0 && is_group(g))
+    rc = group_replicate(g, offset, sb.p, bsk_bytes, with_ksk ? sk.p : nullptr, ksk_bytes, st.p, tv_bytes);
+  set_device(c);
   s0.release(); s1.release(); sb.release(); sk.release(); st.release();
-  if (e != cudaSuccess) return fail(c, TFHE_ERR_CUDA, "key generation: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(g, TFHE_ERR_CUDA, "key generation: %s", cudaGetErrorString(e));
+  if (rc && is_group(g) && g->err.empty()) g->err = c->err;
   return rc;
 }
 
@@ -855,24 +1016,26 @@ int tfhe_bootstrap_batch_device(tfhe_ctx* c, int64_t count, const uint32_t* d_ct
                                 int64_t nluts, uint32_t* d_ct_out, void* stream) {
   int rc = check_ready(c, true);
   if (rc) return rc;
+  if (is_group(c)) return fail(c, TFHE_ERR_ARG, "device-buffer entry points need a single-device context");
   if (count < 0 || (count > 0 && (!d_ct_in || !d_ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
   if (d_luts && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
   if ((rc = set_device(c))) return rc;
   return bootstrap_device(c, count, d_ct_in, d_luts, nluts, d_ct_out, (cudaStream_t)stream);
 }
 
-// ops is a HOST array (one byte per gate); ciphertext pointers are device pointers.
-int tfhe_gate_batch_device(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* d_a,
-                           const uint32_t* d_b, const uint32_t* d_c, uint32_t* d_out, void* stream) {
-  int rc = check_ready(c, true);
-  if (rc) return rc;
-  if (count < 0 || !ops || (nops != 1 && nops != count) || (count > 0 && (!d_a || !d_out)))
-    return fail(c, TFHE_ERR_ARG, "bad batch arguments");
-  if (count == 0) return TFHE_OK;
-  if ((rc = set_device(c))) return rc;
-  cudaStream_t s = (cudaStream_t)stream;
+}  // extern "C"
+
+namespace {
+
+// One batch of gates on device buffers, enqueued on `s`, never synchronised.  `ops` is HOST memory.
+// Every gate that bootstraps becomes a JOB of a compacted batch: plain two-input gates first, then AND(a,b) of every MUX,
+// then ANDNY(a,c) of every MUX (gates.go:107-114 with AND(NOT a, c) == ANDNY(a, c)); the second MUX level is
+// OR(job, job).  Prepared rows are written straight into the compacted batch (never into d_out), NOT / COPY results
+// straight into d_out, so d_out may be the very same buffer as d_a, d_b or d_c.  The index lists travel through the
+// slot's pinned host buffer; `sl.idx_done` guards its reuse.
+int gate_batch_device_impl(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* d_a,
+                           const uint32_t* d_b, const uint32_t* d_c, uint32_t* d_out, cudaStream_t s, Slot& sl) {
   const int n1 = c->P.n + 1;
-  // classify on the host
   bool any_mux = false, any_unary = false, any_boot = false;
   for (int64_t g = 0; g < nops; g++) {
     const uint8_t op = ops[g];
@@ -883,70 +1046,159 @@ int tfhe_gate_batch_device(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64
   }
   if ((any_boot || any_mux) && !d_b) return fail(c, TFHE_ERR_ARG, "b is required by two-input gates");
   if (any_mux && !d_c) return fail(c, TFHE_ERR_ARG, "c is required by MUX gates");
-  CK(c, c->ops_dev.reserve((size_t)nops));
-  CK(c, cudaMemcpyAsync(c->ops_dev.p, ops, (size_t)nops, cudaMemcpyHostToDevice, s));
-  CK(c, c->prep.reserve((size_t)2 * count * n1 * 4));
-  uint32_t* prep0 = c->prep.as<uint32_t>();
-  uint32_t* prep1 = prep0 + (size_t)count * n1;
-  if (!any_mux && !any_unary) {  // fast path: every gate is one bootstrap, rows stay in place
-    gate_prepare_kernel<<<(unsigned)count, 256, 0, s>>>(count, c->ops_dev.as<uint8_t>(), nops, d_a, d_b, d_c, prep0, prep1,
-                                                        c->P.n);
+  const bool uniform = nops == 1;
+  // host staging: [job_of: count ints][src1 + muxg: <= count ints][opcodes: count bytes], pinned, one per slot
+  const size_t need = (size_t)(uniform && !any_mux && !any_unary ? 0 : 2 * count) * sizeof(int) + (uniform ? 0 : (size_t)count);
+  if (need) {
+    if (sl.idx_pending) { CK(c, cudaEventSynchronize(sl.idx_done)); sl.idx_pending = false; }
+    if (need > sl.h_idx_cap) {
+      if (sl.h_idx) cudaFreeHost(sl.h_idx);
+      sl.h_idx = nullptr; sl.h_idx_cap = 0;
+      CK(c, cudaMallocHost(&sl.h_idx, need + need / 4));
+      sl.h_idx_cap = need + need / 4;
+    }
+    CK(c, c->idx_a.reserve(need));
+  }
+  const uint8_t* d_ops = nullptr;
+  if (!uniform) {  // opcodes: copied out of the caller's buffer before the call returns
+    uint8_t* h = reinterpret_cast<uint8_t*>(sl.h_idx) + (size_t)(any_mux || any_unary ? 2 * count : 0) * sizeof(int);
+    memcpy(h, ops, (size_t)count);
+    d_ops = c->idx_a.as<uint8_t>() + (h - reinterpret_cast<uint8_t*>(sl.h_idx));
+  }
+  if (!any_mux && !any_unary) {  // fast path: job g = gate g, the key switch writes d_out directly
+    if (!uniform) {
+      CK(c, cudaMemcpyAsync(c->idx_a.p, sl.h_idx, need, cudaMemcpyHostToDevice, s));
+      CK(c, cudaEventRecord(sl.idx_done, s));
+      sl.idx_pending = true;
+    }
+    CK(c, c->prep.reserve((size_t)count * n1 * 4));
+    gate_prepare_kernel<<<(unsigned)count, 256, 0, s>>>(count, d_ops, uniform ? (int)ops[0] : -1, d_a, d_b, d_c, nullptr,
+                                                        c->prep.as<uint32_t>(), 0, 0, d_out, c->P.n);
     c->launches++;
     CK(c, cudaGetLastError());
-    return bootstrap_device(c, count, prep0, nullptr, 0, d_out, s);
+    return bootstrap_device(c, count, c->prep.as<uint32_t>(), nullptr, 0, d_out, s);
   }
-  // general path: NOT/COPY results go straight to d_out; bootstrapped jobs are compacted by index lists
-  gate_prepare_kernel<<<(unsigned)count, 256, 0, s>>>(count, c->ops_dev.as<uint8_t>(), nops, d_a, d_b, d_c, d_out, prep1,
-                                                      c->P.n);
+  int* job_of = sl.h_idx;
+  int* lists = sl.h_idx + count;
+  int64_t nb = 0, nm = 0;
+  for (int64_t g = 0; g < count; g++) {
+    const uint8_t op = ops[uniform ? 0 : g];
+    if (op < TFHE_OP_MUX) nb++;
+    else if (op == TFHE_OP_MUX) nm++;
+  }
+  int* src1 = lists;
+  int* muxg = lists + nb;
+  int64_t ib = 0, im = 0;
+  for (int64_t g = 0; g < count; g++) {
+    const uint8_t op = ops[uniform ? 0 : g];
+    if (op < TFHE_OP_MUX) { job_of[g] = (int)ib; src1[ib++] = (int)g; }
+    else if (op == TFHE_OP_MUX) { job_of[g] = (int)im; muxg[im++] = (int)g; }
+    else job_of[g] = -1;
+  }
+  CK(c, cudaMemcpyAsync(c->idx_a.p, sl.h_idx, need, cudaMemcpyHostToDevice, s));
+  CK(c, cudaEventRecord(sl.idx_done, s));
+  sl.idx_pending = true;
+  const int* d_job_of = c->idx_a.as<int>();
+  const int* d_src1 = d_job_of + count;
+  const int* d_muxg = d_src1 + nb;
+  const int64_t j1 = nb + 2 * nm;
+  CK(c, c->prep.reserve((size_t)std::max<int64_t>(j1, 1) * n1 * 4));
+  CK(c, c->tmp.reserve((size_t)std::max<int64_t>(j1, 1) * n1 * 4));
+  uint32_t* in1 = c->prep.as<uint32_t>();
+  uint32_t* out1 = c->tmp.as<uint32_t>();
+  gate_prepare_kernel<<<(unsigned)count, 256, 0, s>>>(count, d_ops, uniform ? (int)ops[0] : -1, d_a, d_b, d_c, d_job_of, in1,
+                                                      (long long)nb, (long long)nm, d_out, c->P.n);
   c->launches++;
   CK(c, cudaGetLastError());
-  // (prepared rows of two-input gates now sit in d_out[g]; MUX second operand in prep1[g])
-  std::vector<int> src1, dst1, muxg;  // level-1 jobs: src row in the virtual space [d_out | prep1], dst likewise in [d_out | tmp]
-  for (int64_t g = 0; g < count; g++) {
-    const uint8_t op = ops[nops == 1 ? 0 : g];
-    if (op == TFHE_OP_MUX) { muxg.push_back((int)g); }
-    else if (op < TFHE_OP_MUX) { src1.push_back((int)g); }
-  }
-  const int64_t nb = (int64_t)src1.size(), nm = (int64_t)muxg.size();
-  const int64_t j1 = nb + 2 * nm;
-  // gather level-1 inputs into a contiguous batch: [plain gates | mux AND(a,b) | mux ANDNY(a,c)]
-  CK(c, c->prep2.reserve((size_t)(j1 > 0 ? j1 : 1) * n1 * 4));
-  CK(c, c->tmp.reserve((size_t)(j1 > 0 ? j1 : 1) * n1 * 4));
-  CK(c, c->idx_a.reserve((size_t)(count + 1) * sizeof(int)));
-  CK(c, c->idx_b.reserve((size_t)(count + 1) * sizeof(int)));
-  uint32_t* in1 = c->prep2.as<uint32_t>();
-  uint32_t* out1 = c->tmp.as<uint32_t>();
+  int rc;
+  if (j1 && (rc = bootstrap_device(c, j1, in1, nullptr, 0, out1, s))) return rc;
   if (nb) {
-    CK(c, cudaMemcpyAsync(c->idx_a.p, src1.data(), nb * sizeof(int), cudaMemcpyHostToDevice, s));
-    gather_rows_kernel<<<(unsigned)nb, 128, 0, s>>>(d_out, c->idx_a.as<int>(), in1, n1);
+    scatter_rows_kernel<<<(unsigned)nb, 128, 0, s>>>(out1, d_src1, d_out, n1);
     c->launches++;
   }
-  if (nm) {
-    CK(c, cudaMemcpyAsync(c->idx_b.p, muxg.data(), nm * sizeof(int), cudaMemcpyHostToDevice, s));
-    gather_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(d_out, c->idx_b.as<int>(), in1 + (size_t)nb * n1, n1);
-    gather_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(prep1, c->idx_b.as<int>(), in1 + (size_t)(nb + nm) * n1, n1);
-    c->launches += 2;
-  }
-  CK(c, cudaGetLastError());
-  if ((rc = bootstrap_device(c, j1, in1, nullptr, 0, out1, s))) return rc;
-  if (nb) {
-    scatter_rows_kernel<<<(unsigned)nb, 128, 0, s>>>(out1, c->idx_a.as<int>(), d_out, n1);
-    c->launches++;
-  }
-  if (nm) {  // level 2: OR(andAB, andNotAC)
-    uint32_t* in2 = in1;  // reuse
+  if (nm) {  // level 2: OR(AND(a,b), ANDNY(a,c)); level-1 inputs are consumed by now (stream order), reuse their rows
+    uint32_t* in2 = in1;
     mux_or_prepare_kernel<<<(unsigned)nm, 256, 0, s>>>(out1 + (size_t)nb * n1, out1 + (size_t)(nb + nm) * n1, in2, c->P.n);
     c->launches++;
     CK(c, cudaGetLastError());
-    uint32_t* out2 = out1;  // level-1 outputs are consumed by now (stream order)
+    uint32_t* out2 = out1;
     if ((rc = bootstrap_device(c, nm, in2, nullptr, 0, out2, s))) return rc;
-    scatter_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(out2, c->idx_b.as<int>(), d_out, n1);
+    scatter_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(out2, d_muxg, d_out, n1);
     c->launches++;
   }
   CK(c, cudaGetLastError());
-  // index vectors are host temporaries consumed by async copies: make sure the copies are done
-  CK(c, cudaStreamSynchronize(s));
   return TFHE_OK;
+}
+
+// --- pipelined host-buffer calls -------------------------------------------------------------------------------------
+// A host-buffer batch larger than ~1.5 pipeline chunks is cut into chunks that flow through two staging slots on three
+// streams (copy in / compute / copy out), so that the transfers of chunk k+1 and k-1 overlap the compute of chunk k
+// and device staging stays bounded whatever the batch size.  `in[]` are the per-row input arrays (a, b, c / ct, luts).
+struct HostIn { const void* p; size_t row_bytes; DevBuf Slot::*buf; };
+
+template <class Compute>  // Compute(slot, g0, cnt) enqueues the chunk's kernels on c->stream, reading slot.*, writing slot.out
+int run_pipelined(tfhe_ctx* c, int64_t count, const HostIn* in, int nin, void* out, size_t out_row_bytes, Compute compute) {
+  const int64_t CH = c->pipe_chunk;
+  const int64_t nch = count <= CH + CH / 2 ? 1 : (count + CH - 1) / CH;
+  const int64_t per = (count + nch - 1) / nch;
+  for (int k = 0; k < (nch > 1 ? 2 : 1); k++) {
+    Slot& sl = c->slot[k];
+    for (int q = 0; q < nin; q++)
+      if (in[q].p) CK(c, (sl.*(in[q].buf)).reserve((size_t)per * in[q].row_bytes));
+    CK(c, sl.out.reserve((size_t)per * out_row_bytes));
+  }
+  cudaStream_t s_in = nch > 1 ? c->s_in : c->stream, s_out = nch > 1 ? c->s_out : c->stream;
+  auto copy_out = [&](int64_t k) -> int {
+    Slot& sl = c->slot[k & 1];
+    const int64_t g0 = k * per, cnt = std::min<int64_t>(per, count - g0);
+    if (nch > 1) CK(c, cudaStreamWaitEvent(s_out, sl.comp_done, 0));
+    CK(c, cudaMemcpyAsync(reinterpret_cast<char*>(out) + (size_t)g0 * out_row_bytes, sl.out.p, (size_t)cnt * out_row_bytes,
+                          cudaMemcpyDeviceToHost, s_out));
+    if (nch > 1) CK(c, cudaEventRecord(sl.out_done, s_out));
+    return 0;
+  };
+  for (int64_t k = 0; k < nch; k++) {
+    Slot& sl = c->slot[k & 1];
+    const int64_t g0 = k * per, cnt = std::min<int64_t>(per, count - g0);
+    if (nch > 1 && k >= 2) CK(c, cudaStreamWaitEvent(s_in, sl.comp_done, 0));  // chunk k-2 has consumed this slot's inputs
+    for (int q = 0; q < nin; q++)
+      if (in[q].p)
+        CK(c, cudaMemcpyAsync((sl.*(in[q].buf)).p, reinterpret_cast<const char*>(in[q].p) + (size_t)g0 * in[q].row_bytes,
+                              (size_t)cnt * in[q].row_bytes, cudaMemcpyHostToDevice, s_in));
+    if (nch > 1) {
+      CK(c, cudaEventRecord(sl.in_done, s_in));
+      CK(c, cudaStreamWaitEvent(c->stream, sl.in_done, 0));
+      if (k >= 2) CK(c, cudaStreamWaitEvent(c->stream, sl.out_done, 0));  // chunk k-2's results have left this slot
+    }
+    int rc = compute(sl, g0, cnt);
+    if (rc) return rc;
+    if (nch > 1) CK(c, cudaEventRecord(sl.comp_done, c->stream));
+    // results of the PREVIOUS chunk go out only now: with pageable host memory the copy blocks this thread until that
+    // chunk is done, and the chunk just enqueued keeps the GPU busy meanwhile
+    if (k >= 1 && (rc = copy_out(k - 1))) return rc;
+  }
+  int rc = copy_out(nch - 1);
+  if (rc) return rc;
+  CK(c, cudaStreamSynchronize(s_out));
+  if (nch > 1) CK(c, cudaStreamSynchronize(c->stream));
+  return TFHE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ops is a HOST array (one byte per gate, or one for all); ciphertext pointers are device pointers.
+int tfhe_gate_batch_device(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* d_a,
+                           const uint32_t* d_b, const uint32_t* d_c, uint32_t* d_out, void* stream) {
+  int rc = check_ready(c, true);
+  if (rc) return rc;
+  if (is_group(c)) return fail(c, TFHE_ERR_ARG, "device-buffer entry points need a single-device context");
+  if (count < 0 || !ops || (nops != 1 && nops != count) || (count > 0 && (!d_a || !d_out)))
+    return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (count == 0) return TFHE_OK;
+  if ((rc = set_device(c))) return rc;
+  return gate_batch_device_impl(c, count, ops, nops, d_a, d_b, d_c, d_out, (cudaStream_t)stream, c->slot[0]);
 }
 
 // ---- host-buffer API --------------------------------------------------------------------------------
@@ -963,17 +1215,24 @@ int tfhe_bootstrap_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, cons
   if (count < 0 || (count > 0 && (!ct_in || !ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
   if (luts && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
   if (count == 0) return TFHE_OK;
+  const size_t row = (size_t)(c->P.n + 1) * 4, lrow = (size_t)2 * c->P.N * 4;
+  if (is_group(c)) {
+    const std::vector<int64_t> b = shard_bounds((int)c->kids.size(), count, nullptr, 0);
+    return for_each_kid(c, [&](int d) {
+      const int64_t g0 = b[d], cnt = b[d + 1] - b[d];
+      return tfhe_bootstrap_batch(c->kids[d], cnt, ct_in + (size_t)g0 * (c->P.n + 1),
+                                  luts ? luts + (nluts == 1 ? 0 : (size_t)g0 * 2 * c->P.N) : nullptr, luts ? (nluts == 1 ? 1 : cnt) : 0,
+                                  ct_out + (size_t)g0 * (c->P.n + 1));
+    });
+  }
   if ((rc = set_device(c))) return rc;
-  const size_t bytes = (size_t)count * (c->P.n + 1) * 4;
-  if ((rc = h2d(c, c->h2d_a, ct_in, bytes))) return rc;
-  if (luts && (rc = h2d(c, c->h2d_luts, luts, (size_t)nluts * 2 * c->P.N * 4))) return rc;
-  CK(c, c->d2h_out.reserve(bytes));
-  if ((rc = bootstrap_device(c, count, c->h2d_a.as<uint32_t>(), luts ? c->h2d_luts.as<uint32_t>() : nullptr, nluts,
-                             c->d2h_out.as<uint32_t>(), c->stream)))
-    return rc;
-  CK(c, cudaMemcpyAsync(ct_out, c->d2h_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
-  return TFHE_OK;
+  const bool per_ct = luts && nluts != 1;
+  if (luts && !per_ct && (rc = h2d(c, c->h2d_luts, luts, lrow))) return rc;
+  const HostIn in[2] = {{ct_in, row, &Slot::a}, {per_ct ? luts : nullptr, lrow, &Slot::luts}};
+  return run_pipelined(c, count, in, 2, ct_out, row, [&](Slot& sl, int64_t, int64_t cnt) {
+    return bootstrap_device(c, cnt, sl.a.as<uint32_t>(), luts ? (per_ct ? sl.luts.as<uint32_t>() : c->h2d_luts.as<uint32_t>()) : nullptr,
+                            luts ? (per_ct ? cnt : 1) : 0, sl.out.as<uint32_t>(), c->stream);
+  });
 }
 
 int tfhe_gate_batch(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* a, const uint32_t* b,
@@ -983,18 +1242,24 @@ int tfhe_gate_batch(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops
   if (count < 0 || !ops || (nops != 1 && nops != count) || (count > 0 && (!a || !out)))
     return fail(c, TFHE_ERR_ARG, "bad batch arguments");
   if (count == 0) return TFHE_OK;
+  const size_t n1 = (size_t)c->P.n + 1;
+  if (is_group(c)) {  // shards of equal bootstrap cost (MUX = 3), one host thread per device
+    for (int64_t g = 0; g < nops; g++)
+      if (ops[g] > TFHE_OP_COPY) return fail(c, TFHE_ERR_ARG, "unknown opcode %d at gate %lld", (int)ops[g], (long long)g);
+    const std::vector<int64_t> bd = shard_bounds((int)c->kids.size(), count, ops, nops);
+    return for_each_kid(c, [&](int d) {
+      const int64_t g0 = bd[d], cnt = bd[d + 1] - bd[d];
+      return tfhe_gate_batch(c->kids[d], cnt, ops + (nops == 1 ? 0 : g0), nops == 1 ? 1 : cnt, a + g0 * n1, b ? b + g0 * n1 : nullptr,
+                             cc ? cc + g0 * n1 : nullptr, out + g0 * n1);
+    });
+  }
   if ((rc = set_device(c))) return rc;
-  const size_t bytes = (size_t)count * (c->P.n + 1) * 4;
-  if ((rc = h2d(c, c->h2d_a, a, bytes))) return rc;
-  if (b && (rc = h2d(c, c->h2d_b, b, bytes))) return rc;
-  if (cc && (rc = h2d(c, c->h2d_c, cc, bytes))) return rc;
-  CK(c, c->d2h_out.reserve(bytes));
-  if ((rc = tfhe_gate_batch_device(c, count, ops, nops, c->h2d_a.as<uint32_t>(), b ? c->h2d_b.as<uint32_t>() : nullptr,
-                                   cc ? c->h2d_c.as<uint32_t>() : nullptr, c->d2h_out.as<uint32_t>(), c->stream)))
-    return rc;
-  CK(c, cudaMemcpyAsync(out, c->d2h_out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
-  return TFHE_OK;
+  const HostIn in[3] = {{a, n1 * 4, &Slot::a}, {b, n1 * 4, &Slot::b}, {cc, n1 * 4, &Slot::c}};
+  return run_pipelined(c, count, in, 3, out, n1 * 4, [&](Slot& sl, int64_t g0, int64_t cnt) {
+    return gate_batch_device_impl(c, cnt, ops + (nops == 1 ? 0 : g0), nops == 1 ? 1 : cnt, sl.a.as<uint32_t>(),
+                                  b ? sl.b.as<uint32_t>() : nullptr, cc ? sl.c.as<uint32_t>() : nullptr, sl.out.as<uint32_t>(),
+                                  c->stream, sl);
+  });
 }
 
 int tfhe_blind_rotate_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* luts, int64_t nluts,
@@ -1004,23 +1269,31 @@ int tfhe_blind_rotate_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, c
   if (count < 0 || (count > 0 && (!ct_in || !trlwe_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
   if (luts && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
   if (count == 0) return TFHE_OK;
+  const size_t row = (size_t)(c->P.n + 1) * 4, lrow = (size_t)2 * c->P.N * 4;
+  if (is_group(c)) {
+    const std::vector<int64_t> b = shard_bounds((int)c->kids.size(), count, nullptr, 0);
+    return for_each_kid(c, [&](int d) {
+      const int64_t g0 = b[d], cnt = b[d + 1] - b[d];
+      return tfhe_blind_rotate_batch(c->kids[d], cnt, ct_in + (size_t)g0 * (c->P.n + 1),
+                                     luts ? luts + (nluts == 1 ? 0 : (size_t)g0 * 2 * c->P.N) : nullptr, luts ? (nluts == 1 ? 1 : cnt) : 0,
+                                     trlwe_out + (size_t)g0 * 2 * c->P.N);
+    });
+  }
   if ((rc = set_device(c))) return rc;
-  const size_t in_bytes = (size_t)count * (c->P.n + 1) * 4, out_bytes = (size_t)count * 2 * c->P.N * 4;
-  if ((rc = h2d(c, c->h2d_a, ct_in, in_bytes))) return rc;
-  if (luts && (rc = h2d(c, c->h2d_luts, luts, (size_t)nluts * 2 * c->P.N * 4))) return rc;
-  CK(c, c->d2h_out.reserve(out_bytes));
-  if ((rc = launch_blind_rotate(c, count, c->h2d_a.as<uint32_t>(), luts ? c->h2d_luts.as<uint32_t>() : nullptr, nluts,
-                                c->d2h_out.as<uint32_t>(), 0, c->stream)))
-    return rc;
-  CK(c, cudaMemcpyAsync(trlwe_out, c->d2h_out.p, out_bytes, cudaMemcpyDeviceToHost, c->stream));
-  CK(c, cudaStreamSynchronize(c->stream));
-  return TFHE_OK;
+  const bool per_ct = luts && nluts != 1;
+  if (luts && !per_ct && (rc = h2d(c, c->h2d_luts, luts, lrow))) return rc;
+  const HostIn in[2] = {{ct_in, row, &Slot::a}, {per_ct ? luts : nullptr, lrow, &Slot::luts}};
+  return run_pipelined(c, count, in, 2, trlwe_out, lrow, [&](Slot& sl, int64_t, int64_t cnt) {
+    return launch_blind_rotate(c, cnt, sl.a.as<uint32_t>(), luts ? (per_ct ? sl.luts.as<uint32_t>() : c->h2d_luts.as<uint32_t>()) : nullptr,
+                               luts ? (per_ct ? cnt : 1) : 0, sl.out.as<uint32_t>(), 0, c->stream);
+  });
 }
 
 int tfhe_cmux_batch(tfhe_ctx* c, int64_t count, int32_t bsk_index, const uint32_t* ct0, const uint32_t* ct1,
                     uint32_t* out) {
   int rc = check_ready(c, false);
   if (rc) return rc;
+  if (is_group(c)) return tfhe_cmux_batch(c->kids[0], count, bsk_index, ct0, ct1, out) ? fail(c, TFHE_ERR_CUDA, "%s", c->kids[0]->err.c_str()) : TFHE_OK;
   if (count < 0 || bsk_index < 0 || bsk_index >= c->P.n || (count > 0 && (!ct1 || !out)))
     return fail(c, TFHE_ERR_ARG, "bad cmux arguments");
   if (count == 0) return TFHE_OK;
@@ -1045,6 +1318,7 @@ int tfhe_cmux_batch(tfhe_ctx* c, int64_t count, int32_t bsk_index, const uint32_
 
 int tfhe_sample_extract_batch(tfhe_ctx* c, int64_t count, const uint32_t* trlwe_in, uint32_t* lwe_out) {
   if (!c) return TFHE_ERR_ARG;
+  if (is_group(c)) return tfhe_sample_extract_batch(c->kids[0], count, trlwe_in, lwe_out) ? fail(c, TFHE_ERR_CUDA, "%s", c->kids[0]->err.c_str()) : TFHE_OK;
   if (count < 0 || (count > 0 && (!trlwe_in || !lwe_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
   if (count == 0) return TFHE_OK;
   int rc = set_device(c);
@@ -1063,6 +1337,7 @@ int tfhe_sample_extract_batch(tfhe_ctx* c, int64_t count, const uint32_t* trlwe_
 int tfhe_key_switch_batch(tfhe_ctx* c, int64_t count, const uint32_t* lwe_in, uint32_t* ct_out) {
   int rc = check_ready(c, true);
   if (rc) return rc;
+  if (is_group(c)) return tfhe_key_switch_batch(c->kids[0], count, lwe_in, ct_out) ? fail(c, TFHE_ERR_CUDA, "%s", c->kids[0]->err.c_str()) : TFHE_OK;
   if (count < 0 || (count > 0 && (!lwe_in || !ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
   if (count == 0) return TFHE_OK;
   if ((rc = set_device(c))) return rc;
@@ -1086,6 +1361,26 @@ int tfhe_circuit_run(tfhe_ctx* c, int64_t instances, int32_t n_inputs, int32_t n
   if (instances < 0 || n_inputs < 0 || n_gates < 0 || n_outputs < 0 || (n_gates > 0 && !gates) ||
       (n_inputs > 0 && instances > 0 && !inputs) || (n_outputs > 0 && (!output_wires || (instances > 0 && !outputs))))
     return fail(c, TFHE_ERR_ARG, "bad circuit arguments");
+  if (is_group(c)) {  // whole instances per device: no ciphertext ever crosses GPUs (wires are [wire][instance][n+1])
+    const int nd = (int)c->kids.size();
+    const size_t n1g = (size_t)c->P.n + 1;
+    std::vector<std::vector<uint32_t>> in_sh(nd), out_sh(nd);
+    std::vector<int64_t> bnd(nd + 1);
+    for (int d = 0; d <= nd; d++) bnd[d] = instances * d / nd;
+    rc = for_each_kid(c, [&](int d) -> int {
+      const int64_t i0 = bnd[d], cnt = bnd[d + 1] - bnd[d];
+      in_sh[d].resize((size_t)n_inputs * cnt * n1g);
+      for (int w = 0; w < n_inputs; w++)
+        if (cnt) memcpy(in_sh[d].data() + (size_t)w * cnt * n1g, inputs + ((size_t)w * instances + i0) * n1g, (size_t)cnt * n1g * 4);
+      out_sh[d].resize((size_t)n_outputs * cnt * n1g);
+      const int r = tfhe_circuit_run(c->kids[d], cnt, n_inputs, n_gates, gates, in_sh[d].data(), n_outputs, output_wires, out_sh[d].data());
+      if (r) return r;
+      for (int k = 0; k < n_outputs; k++)
+        if (cnt) memcpy(outputs + ((size_t)k * instances + i0) * n1g, out_sh[d].data() + (size_t)k * cnt * n1g, (size_t)cnt * n1g * 4);
+      return 0;
+    });
+    return rc;
+  }
   if ((rc = set_device(c))) return rc;
   // 1. validate (topological order, single assignment), expand MUX, compute depths
   int n_wires = n_inputs;
@@ -1181,6 +1476,7 @@ int tfhe_circuit_run(tfhe_ctx* c, int64_t instances, int32_t n_inputs, int32_t n
 static int poly_call(tfhe_ctx* c, int mode, int64_t count, const void* in0, size_t in0_bytes, const void* in1,
                      size_t in1_bytes, void* out, size_t out_bytes) {
   if (!c) return TFHE_ERR_ARG;
+  if (is_group(c)) c = c->kids[0];
   if (count < 0 || (count > 0 && (!in0 || !out || (mode == 2 && !in1)))) return fail(c, TFHE_ERR_ARG, "bad polynomial batch arguments");
   if (count == 0) return TFHE_OK;
   int rc = set_device(c);
@@ -1217,15 +1513,33 @@ int tfhe_mul_poly_batch(tfhe_ctx* c, int64_t count, const uint32_t* p0, const ui
   return poly_call(c, 2, count, p0, (size_t)count * N * 4, p1, (size_t)count * N * 4, out, (size_t)count * N * 4);
 }
 
-int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) { return c ? c->launches : 0; }
+int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) {
+  if (!c) return 0;
+  int64_t total = c->launches;
+  for (const tfhe_ctx* k : c->kids) total += k->launches;
+  return total;
+}
+
+// a setting applied to a group goes to every device
+#define GROUP_FORWARD(c, call)                                                   \
+  if ((c) && is_group(c)) {                                                      \
+    for (tfhe_ctx* k__ : (c)->kids) {                                            \
+      tfhe_ctx* kid = k__;                                                       \
+      const int rc__ = (call);                                                   \
+      if (rc__) { (c)->err = kid->err; return rc__; }                            \
+    }                                                                            \
+    return TFHE_OK;                                                              \
+  }
 
 int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
+  GROUP_FORWARD(c, tfhe_ctx_set_key_switch_variant(kid, variant));
   if (!c || variant < 0 || variant > 2) return fail(c, TFHE_ERR_ARG, "key-switch variant must be 0 (auto), 1 (gather) or 2 (tensor core)");
   c->ks_variant = variant;
   return TFHE_OK;
 }
 
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
+  GROUP_FORWARD(c, tfhe_ctx_set_blind_rotate_variant(kid, variant));
   if (!c) return TFHE_ERR_ARG;
   if (variant == 0) { c->br_variant = 0; c->br_auto_lat = true; return TFHE_OK; }
   if (variant == 10) { c->br_variant = 0; c->br_auto_lat = false; return TFHE_OK; }  // throughput kernel at every batch size
@@ -1264,12 +1578,22 @@ int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
 
 // CMUX steps per work item of the persistent throughput kernel: 0 = automatic, >= n = whole gates per item.
 int tfhe_ctx_set_blind_rotate_chunk_steps(tfhe_ctx* c, int steps) {
+  GROUP_FORWARD(c, tfhe_ctx_set_blind_rotate_chunk_steps(kid, steps));
   if (!c || steps < 0) return fail(c, TFHE_ERR_ARG, "chunk steps must be >= 0");
   c->br_chunk_steps = steps;
   return TFHE_OK;
 }
 
+// ciphertexts per chunk of the pipelined host-buffer calls (default 16384; batches up to 1.5 chunks run unchunked)
+int tfhe_ctx_set_pipeline_chunk(tfhe_ctx* c, int64_t rows) {
+  GROUP_FORWARD(c, tfhe_ctx_set_pipeline_chunk(kid, rows));
+  if (!c || rows < 1) return fail(c, TFHE_ERR_ARG, "pipeline chunk must be >= 1");
+  c->pipe_chunk = rows;
+  return TFHE_OK;
+}
+
 int tfhe_ctx_set_timing(tfhe_ctx* c, int enable) {
+  GROUP_FORWARD(c, tfhe_ctx_set_timing(kid, enable));
   if (!c) return TFHE_ERR_ARG;
   c->timing = enable != 0;
   return TFHE_OK;
@@ -1277,6 +1601,16 @@ int tfhe_ctx_set_timing(tfhe_ctx* c, int enable) {
 
 int tfhe_ctx_collect_timing(tfhe_ctx* c, double out[4]) {
   if (!c || !out) return TFHE_ERR_ARG;
+  if (is_group(c)) {  // sums over the devices (they run concurrently: divide by tfhe_ctx_device_count for a per-device mean)
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    for (tfhe_ctx* k : c->kids) {
+      double t[4];
+      const int r = tfhe_ctx_collect_timing(k, t);
+      if (r) { c->err = k->err; return r; }
+      for (int q = 0; q < 4; q++) out[q] += t[q];
+    }
+    return TFHE_OK;
+  }
   int rc = set_device(c);
   if (rc) return rc;
   out[0] = out[1] = out[2] = out[3] = 0.0;
@@ -1289,6 +1623,47 @@ int tfhe_ctx_collect_timing(tfhe_ctx* c, double out[4]) {
     c->ev_free.push_back(ev);
   }
   c->ev_live.clear();
+  return TFHE_OK;
+}
+
+// Measured FP64 throughput of `device`: out = {TFLOP/s (2 flops per DFMA), thread-DFMA per clock per SM at the
+// driver-reported SM clock, that clock in MHz}.  ~0.1 s.
+int tfhe_fp64_peak_probe(int device, double out[3]) {
+  if (!out) return TFHE_ERR_ARG;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, TFHE_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  int sms = 0, khz = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+  double *d = nullptr, *in = nullptr;
+  if ((e = cudaMalloc(&d, 8)) != cudaSuccess || (e = cudaMalloc(&in, 8 * 32)) != cudaSuccess) {
+    if (d) cudaFree(d);
+    return fail(nullptr, TFHE_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+  }
+  const double h[2] = {0.999999, 1e-9};
+  cudaMemset(in, 0, 8 * 32);
+  cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = sms * 8, iters = 1 << 15;  // 8 x 256 threads per SM = 16 warps per scheduler
+  fp64_probe_kernel<<<blocks, 256>>>(d, in, 64);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; rep++) {
+    cudaEventRecord(e0);
+    fp64_probe_kernel<<<blocks, 256>>>(d, in, iters);
+    cudaEventRecord(e1);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double dfma = (double)iters * 64.0 * 256.0 * blocks;
+    if (ms > 0.f) best = std::max(best, dfma / (ms * 1e-3));
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d); cudaFree(in);
+  if (e != cudaSuccess) return fail(nullptr, TFHE_ERR_CUDA, "fp64 probe: %s", cudaGetErrorString(e));
+  out[0] = 2.0 * best / 1e12;
+  out[1] = khz > 0 ? best / ((double)khz * 1e3) / sms : 0.0;
+  out[2] = khz / 1e3;
   return TFHE_OK;
 }
 

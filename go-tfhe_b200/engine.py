@@ -35,15 +35,34 @@ def _ops(ops, count):
 
 
 class Context:
-    def __init__(self, P: ParamSet, device=0):
+    def __init__(self, P: ParamSet, device=0, devices=None):
+        """device: one GPU (tfhe_ctx_create).  devices: a list of GPUs, or "all" — ONE context that shards every host-buffer
+        batch call over them (tfhe_ctx_create_multi)."""
         self.P = P
         self.lib = _native.engine()
         self.h = ctypes.c_void_p()
         tp = _native.TfheParams(P.n, P.N, P.L, P.BGBIT, P.BASEBIT, P.IKS_T)
-        rc = self.lib.tfhe_ctx_create(ctypes.byref(tp), int(device), ctypes.byref(self.h))
+        if devices is None:
+            rc = self.lib.tfhe_ctx_create(ctypes.byref(tp), int(device), ctypes.byref(self.h))
+            what = "tfhe_ctx_create"
+        else:
+            what = "tfhe_ctx_create_multi"
+            if isinstance(devices, str):
+                rc = self.lib.tfhe_ctx_create_multi(ctypes.byref(tp), 0, None, ctypes.byref(self.h))
+            else:
+                arr = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+                rc = self.lib.tfhe_ctx_create_multi(ctypes.byref(tp), len(devices), ctypes.cast(arr, ctypes.c_void_p), ctypes.byref(self.h))
         if rc != 0:
-            raise TfheError("tfhe_ctx_create: %s" % self.lib.tfhe_last_error(None).decode())
+            raise TfheError("%s: %s" % (what, self.lib.tfhe_last_error(None).decode()))
         self.device = device
+
+    @property
+    def device_count(self):
+        return int(self.lib.tfhe_ctx_device_count(self.h))
+
+    def set_pipeline_chunk(self, rows):
+        """ciphertexts per chunk of the pipelined host-buffer calls (results do not depend on it)."""
+        self._ck(self.lib.tfhe_ctx_set_pipeline_chunk(self.h, int(rows)), "tfhe_ctx_set_pipeline_chunk")
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:

@@ -72,6 +72,16 @@ typedef enum {
 /* Creates a context on CUDA device `device` (>= 0).  Replaces evaluator.NewEvaluator
  * (evaluator/evaluator.go:27-35) and the package-global evaluator of gates/gates.go:19-23. */
 int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out);
+/* One context over `ndev` GPUs of this process (devices[0..ndev-1]; devices == NULL: 0..ndev-1; ndev <= 0: every
+ * visible GPU).  The cloud key is uploaded or generated once and replicated to the other devices by peer copies
+ * (NVLink / NVSwitch); the host-buffer batch calls (tfhe_gate_batch, tfhe_bootstrap_batch, tfhe_blind_rotate_batch,
+ * tfhe_circuit_run) shard their batch by index (circuits: by instance) over the devices, one host thread per device,
+ * nothing crosses devices on the hot path.  This is what the goroutine fan-out of trgsw.BatchBlindRotate
+ * (trgsw/trgsw.go:234-252) and gates.Batch* (gates/gates.go:156-312) becomes on a multi-GPU node; results are
+ * identical to a single-device context.  The *_device entry points need a single-device context. */
+int tfhe_ctx_create_multi(const tfhe_params* params, int ndev, const int* devices, tfhe_ctx** out);
+/* Number of GPUs behind `ctx` (1 for tfhe_ctx_create). */
+int tfhe_ctx_device_count(const tfhe_ctx* ctx);
 void tfhe_ctx_destroy(tfhe_ctx* ctx);
 /* Message of the last failure on `ctx` (or of the last failed tfhe_ctx_create if ctx == NULL). */
 const char* tfhe_last_error(const tfhe_ctx* ctx);
@@ -162,11 +172,13 @@ int tfhe_circuit_run(tfhe_ctx* ctx, int64_t instances, int32_t n_inputs, int32_t
                      const uint32_t* inputs, int32_t n_outputs, const int32_t* output_wires, uint32_t* outputs);
 
 /* --- the hot path, device buffers (inputs already resident in HBM) -------------------------- */
-/* Same semantics; pointers are device pointers on the context's device; work is enqueued on
- * `stream` (cudaStream_t, 0 = default) and NOT synchronised. */
+/* Same semantics; ciphertext / LUT pointers are device pointers on the context's device; work is enqueued on
+ * `stream` (cudaStream_t, 0 = default) and NOT synchronised: the call returns as soon as everything is enqueued.
+ * `ops` of tfhe_gate_batch_device is a HOST array (nops in {1, count} opcodes), read before the call returns.
+ * d_out may be the same buffer as d_a, d_b or d_c (prepared ciphertexts go to internal scratch, never to d_out). */
 int tfhe_bootstrap_batch_device(tfhe_ctx* ctx, int64_t count, const uint32_t* d_ct_in, const uint32_t* d_luts,
                                 int64_t nluts, uint32_t* d_ct_out, void* stream);
-int tfhe_gate_batch_device(tfhe_ctx* ctx, int64_t count, const uint8_t* d_ops, int64_t nops, const uint32_t* d_a,
+int tfhe_gate_batch_device(tfhe_ctx* ctx, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* d_a,
                            const uint32_t* d_b, const uint32_t* d_c, uint32_t* d_out, void* stream);
 
 /* --- introspection ---------------------------------------------------------------------------- */
@@ -185,6 +197,10 @@ int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
  * resident blocks still fills the SMs to the end.  0 = automatic (default: whole gates for batches that fit the
  * resident blocks, ~n/14-step items above), >= n = whole gates.  Results do not depend on it. */
 int tfhe_ctx_set_blind_rotate_chunk_steps(tfhe_ctx* ctx, int steps);
+/* Host-buffer batch calls larger than 1.5 chunks of `rows` ciphertexts (default 16384) are pipelined: the transfers of
+ * chunk k+1 (in) and k-1 (out) overlap the kernels of chunk k on separate streams, and device staging stays bounded by
+ * two chunks whatever the batch size.  Results do not depend on it. */
+int tfhe_ctx_set_pipeline_chunk(tfhe_ctx* ctx, int64_t rows);
 /* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default: the contraction wherever it exists), 1 = one block per
  * ciphertext gathering its N*t*(1-1/base) key rows out of L2, 2 = the whole batch as one exact u8 x u8 -> s32
  * contraction on the tensor cores (tcgen05.mma kind::i8 over the byte planes of the key; basebit = 2 parameter sets
@@ -198,6 +214,10 @@ int tfhe_ctx_set_timing(tfhe_ctx* ctx, int enable);
 int tfhe_ctx_collect_timing(tfhe_ctx* ctx, double out[4]);
 /* Algorithmic bytes per bootstrap of SURVEY.md section 8(d): n*2L*2*N*8 + N*t*(1-1/base)*(n+1)*4 + io. */
 int64_t tfhe_ctx_algorithmic_bytes_per_bootstrap(const tfhe_ctx* ctx);
+/* Measured FP64 roof of `device` (bench.py roofline_fp64): independent DFMA chains with reuse-cache operands, the
+ * friendliest instruction mix.  out = {TFLOP/s at 2 flops per DFMA, thread-DFMA per clock per SM at the driver-reported
+ * SM clock, that clock in MHz}.  Takes ~0.1 s. */
+int tfhe_fp64_peak_probe(int device, double out[3]);
 /* Library version string. */
 const char* tfhe_version(void);
 

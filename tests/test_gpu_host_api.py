@@ -1,0 +1,168 @@
+"""GPU tests of the host side of the C ABI added in round 2: the multi-device context (tfhe_ctx_create_multi), the
+pipelined host-buffer calls, the asynchronous device-buffer gate batch (in-place use, host opcodes).  Every check is
+"same words as the plain single-device, single-chunk call", which tests/test_gpu_parity.py pins to the oracle."""
+import importlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+OPS = ["AND", "OR", "XOR", "MUX", "NOT", "COPY", "NAND", "XNOR"]
+
+
+@pytest.fixture(scope="module")
+def T():
+    return importlib.import_module("go-tfhe_b200")
+
+
+@pytest.fixture(scope="module")
+def env(T, keyset):
+    P, sk, ck = keyset("80")
+    ctx = T.Context(T.params.get("80"), 0)
+    ctx.load_cloudkey(ck.offset, ck.bsk_fft, ck.ksk, ck.testvec)
+    yield P, sk, ck, ctx
+    ctx.close()
+
+
+def _mixed(sk, count, seed):
+    rng = np.random.default_rng(seed)
+    A, B, C = (rng.integers(0, 2, count).astype(np.uint8) for _ in range(3))
+    ops = [OPS[k] for k in rng.integers(0, len(OPS), count)]
+    a, b, c = sk.encrypt_bool(A, seed + 1), sk.encrypt_bool(B, seed + 2), sk.encrypt_bool(C, seed + 3)
+    want = []
+    for o, x, y, z in zip(ops, A, B, C):
+        want.append({"AND": x & y, "OR": x | y, "XOR": x ^ y, "MUX": y if x else z, "NOT": 1 - x, "COPY": x,
+                     "NAND": 1 - (x & y), "XNOR": 1 - (x ^ y)}[o])
+    return ops, a, b, c, np.array(want, dtype=np.uint8)
+
+
+def test_pipelined_host_calls_are_chunk_invariant(T, O, env):
+    """tfhe_gate_batch / tfhe_bootstrap_batch / tfhe_blind_rotate_batch cut large host batches into chunks that flow
+    through two staging slots on three streams.  Chunk sizes that give 1, 2, 3 and 6 chunks (incl. a ragged last one)
+    must all give the words of the unchunked call; mixed opcodes exercise the per-chunk index lists."""
+    P, sk, ck, ctx = env
+    count = 41
+    ops, a, b, c, want = _mixed(sk, count, 100)
+    msgs = np.arange(count) % 2
+    ct = sk.encrypt_message(msgs, 2, 7)
+    luts = np.stack([O.gen_lut(P, 2, (lambda x: x) if k % 2 else (lambda x: 1 - x)) for k in range(count)])
+    try:
+        ctx.set_pipeline_chunk(1 << 20)
+        ref_g = ctx.gate_batch(ops, a, b, c)
+        ref_b = ctx.bootstrap_batch(ct, luts)
+        ref_r = ctx.blind_rotate_batch(ct, luts[0])
+        assert np.array_equal(sk.decrypt_bool(ref_g), want)
+        for rows in (27, 20, 14, 7):
+            ctx.set_pipeline_chunk(rows)
+            assert np.array_equal(ctx.gate_batch(ops, a, b, c), ref_g), rows
+            assert np.array_equal(ctx.bootstrap_batch(ct, luts), ref_b), rows
+            assert np.array_equal(ctx.blind_rotate_batch(ct, luts[0]), ref_r), rows
+            assert np.array_equal(ctx.gate_batch("NAND", a, b), ctx.gate_batch(["NAND"] * count, a, b)), rows
+    finally:
+        ctx.set_pipeline_chunk(16384)
+
+
+def test_multi_device_context_matches_single_device(T, O, env):
+    """One context over every visible GPU (tfhe_ctx_create_multi): key uploaded once and replicated by peer copies, host
+    batches sharded by index (MUX-weighted), circuits by instance.  Words must equal the single-device context's —
+    with one visible GPU this still runs the whole group path (sharding, threads, key replication code with no peer)."""
+    P, sk, ck, ctx = env
+    multi = T.Context(T.params.get("80"), devices="all")
+    try:
+        assert multi.device_count >= 1
+        multi.load_cloudkey(ck.offset, ck.bsk_fft, ck.ksk, ck.testvec)
+        count = 37
+        ops, a, b, c, want = _mixed(sk, count, 200)
+        got = multi.gate_batch(ops, a, b, c)
+        assert np.array_equal(got, ctx.gate_batch(ops, a, b, c))
+        assert np.array_equal(sk.decrypt_bool(got), want)
+        ct = sk.encrypt_message(np.arange(count) % 2, 2, 9)
+        lut = O.gen_lut(P, 2, lambda x: 1 - x)
+        assert np.array_equal(multi.bootstrap_batch(ct, lut), ctx.bootstrap_batch(ct, lut))
+        assert np.array_equal(multi.blind_rotate_batch(ct), ctx.blind_rotate_batch(ct))
+        circ = T.circuit.ripple_carry_adder(2)
+        inst = 11
+        rng = np.random.default_rng(5)
+        x, y = rng.integers(0, 4, inst), rng.integers(0, 4, inst)
+        ins = np.stack([sk.encrypt_bool((x >> i) & 1, 30 + i) for i in range(2)] + [sk.encrypt_bool((y >> i) & 1, 40 + i) for i in range(2)])
+        wires = np.concatenate([ins, np.broadcast_to(O.constant(P, False), (1, inst, P.n + 1))])
+        g1 = multi.circuit_run(circ.gates, 5, wires, circ.out_wires)
+        assert np.array_equal(g1, ctx.circuit_run(circ.gates, 5, wires, circ.out_wires))
+        s = sum(sk.decrypt_bool(g1[i]).astype(np.int64) << i for i in range(2))
+        assert np.array_equal(s, (x + y) % 4)
+        with pytest.raises(T.TfheError):  # device pointers have no meaning on a group
+            multi.bootstrap_batch_device(1, 0, 0)
+    finally:
+        multi.close()
+
+
+def test_multi_device_generated_key(T, env):
+    """tfhe_ctx_generate_cloudkey on a group: generated on the first device, replicated, every device computes with it."""
+    P, sk, ck, ctx = env
+    Tm = T
+    sk2 = Tm.key.NewSecretKey(Tm.params.get("80"), 77)
+    multi = Tm.Context(Tm.params.get("80"), devices="all")
+    try:
+        multi.generate_cloudkey(sk2.KeyLv0, sk2.KeyLv1, seed=5, with_ksk=True, export=False)
+        bits = np.arange(64) % 2
+        a, b = Tm.tlwe.EncryptBool(bits, sk2, 1), Tm.tlwe.EncryptBool(1 - bits, sk2, 2)
+        assert np.array_equal(Tm.tlwe.DecryptBool(multi.gate_batch("OR", a, b), sk2), np.ones(64, dtype=np.uint8))
+    finally:
+        multi.close()
+
+
+def test_device_gate_batch_is_async_and_in_place(T, env):
+    """tfhe_gate_batch_device: opcodes are HOST memory, the call only enqueues (mixed batches included), and d_out may
+    be d_a itself — prepared ciphertexts go to internal scratch, so a MUX never re-reads an overwritten input."""
+    torch = pytest.importorskip("torch")
+    P, sk, ck, ctx = env
+    count = 29
+    ops, a, b, c, want = _mixed(sk, count, 300)
+    ref = ctx.gate_batch(ops, a, b, c)
+    dev = torch.device("cuda", 0)
+    da, db, dc = (torch.from_numpy(v.view(np.int32)).to(dev) for v in (a, b, c))
+    stream = torch.cuda.current_stream()
+    ctx.gate_batch_device(count, ops, da.data_ptr(), db.data_ptr(), dc.data_ptr(), da.data_ptr(), stream.cuda_stream)  # in place
+    ctx.gate_batch_device(count, "COPY", da.data_ptr(), None, None, db.data_ptr(), stream.cuda_stream)              # chained, no sync between
+    torch.cuda.synchronize()
+    assert np.array_equal(da.cpu().numpy().view(np.uint32), ref)
+    assert np.array_equal(db.cpu().numpy().view(np.uint32), ref)
+
+
+def test_key_reload_without_ksk_drops_the_old_one(T, env, keyset):
+    """loading a key without a key-switching key must not leave the previous one paired with the new BSK."""
+    P, sk, ck, _ = env
+    fresh = T.Context(T.params.get("80"), 0)
+    try:
+        fresh.load_cloudkey(ck.offset, ck.bsk_fft, ck.ksk, ck.testvec)
+        ct = sk.encrypt_bool([1, 0], 3)
+        fresh.bootstrap_batch(ct)
+        fresh.load_cloudkey(ck.offset, ck.bsk_fft, None, ck.testvec)
+        with pytest.raises(T.TfheError):
+            fresh.bootstrap_batch(ct)
+        assert fresh.blind_rotate_batch(ct).shape == (2, 2, P.N)
+    finally:
+        fresh.close()
+
+
+def test_nonzero_k0_rows_of_an_uploaded_key_are_ignored(T, O, env):
+    """the reference never reads KSK rows with digit 0 (trgsw/keyswitch.go:30); a key that carries garbage
+    there must give the same words on every key-switch path (compacted gather, ordered split gather, tensor cores)."""
+    P, sk, ck, ctx = env
+    dirty = ck.ksk.copy().reshape(-1, P.n + 1)
+    base = 1 << P.basebit
+    dirty[::base] = 0xDEADBEEF
+    other = T.Context(T.params.get("80"), 0)
+    try:
+        other.load_cloudkey(ck.offset, ck.bsk_fft, dirty, ck.testvec)
+        rng = np.random.default_rng(3)
+        for count in (1, 3, 400):  # split gather / gather / chunks of the contraction
+            ext = rng.integers(0, 1 << 32, (count, P.N + 1), dtype=np.uint64).astype(np.uint32)
+            for v in ("gather", "mma"):
+                other.set_key_switch_variant(v)
+                ctx.set_key_switch_variant(v)
+                assert np.array_equal(other.key_switch_batch(ext), ctx.key_switch_batch(ext)), (count, v)
+    finally:
+        ctx.set_key_switch_variant("auto")
+        other.close()
