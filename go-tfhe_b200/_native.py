@@ -26,7 +26,7 @@ ENGINE_SYMBOLS = [
 ]
 CLIENT_SYMBOLS = [
     "tfhe_client_secret_key", "tfhe_client_encrypt_bool", "tfhe_client_decrypt_bool", "tfhe_client_encrypt_message",
-    "tfhe_client_decrypt_message", "tfhe_client_gen_lut", "tfhe_client_cloud_key",
+    "tfhe_client_decrypt_message", "tfhe_client_gen_lut", "tfhe_client_cloud_key", "tfhe_client_chacha20_block",
 ]
 
 _engine = None
@@ -98,6 +98,7 @@ def client():
         lib.tfhe_client_decrypt_message.argtypes = [PP, vp, i64, vp, i32, vp]
         lib.tfhe_client_gen_lut.argtypes = [PP, i32, vp, vp]
         lib.tfhe_client_cloud_key.argtypes = [PP, dbl, dbl, vp, vp, u64, ctypes.c_int, vp, vp, vp, vp]
+        lib.tfhe_client_chacha20_block.argtypes = [vp, ctypes.c_uint32, vp, vp]
         for s in CLIENT_SYMBOLS:
             getattr(lib, s).restype = None
         _client = lib

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 from . import _native, engine
-from .key import _tp
+from .key import _seed, _tp
 
 
 class CloudKey:
@@ -34,7 +34,7 @@ class CloudKey:
         self._ctx = {}
 
 
-def NewCloudKey(secretKey, seed=1, threads=None, with_ksk=True):
+def NewCloudKey(secretKey, seed=None, threads=None, with_ksk=True):
     """cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-31); with_ksk=False ~ NewCloudKeyNoKSK (:34-57)."""
     P = secretKey.P
     off = ctypes.c_uint32(0)
@@ -42,13 +42,13 @@ def NewCloudKey(secretKey, seed=1, threads=None, with_ksk=True):
     ksk = np.zeros((P.ksk_rows, P.n + 1), dtype=np.uint32) if with_ksk else None
     bsk = np.zeros((P.n, 2 * P.L, 2, P.N), dtype=np.float64)
     _native.client().tfhe_client_cloud_key(ctypes.byref(_tp(P)), P.alpha_lv0, P.alpha_lv1, secretKey.KeyLv0.ctypes.data,
-                                           secretKey.KeyLv1.ctypes.data, seed, threads or (os.cpu_count() or 1),
+                                           secretKey.KeyLv1.ctypes.data, _seed(seed), threads or (os.cpu_count() or 1),
                                            ctypes.byref(off), tv.ctypes.data, ksk.ctypes.data if with_ksk else None,
                                            bsk.ctypes.data)
     return CloudKey(P, off.value, tv, ksk, bsk)
 
 
-def NewCloudKeyOnDevice(secretKey, seed=1, device=0, with_ksk=True, export=True):
+def NewCloudKeyOnDevice(secretKey, seed=None, device=0, with_ksk=True, export=True):
     """cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-31) evaluated on the GPU (tfhe_ctx_generate_cloudkey): the
     bootstrapping and key-switching keys are produced in device memory and left loaded in the engine; with export=True
     the returned CloudKey also carries the reference-layout fields (what a Go caller would store), otherwise only the

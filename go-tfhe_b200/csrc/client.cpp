@@ -4,56 +4,66 @@
 // library is the stand-in used where no Go toolchain exists (this image), so that bench.py
 // and the examples can produce valid keys and ciphertexts WITHOUT touching oracle/.
 // It is an independent implementation: integer-exact ring products (the secret keys are
-// binary, so a*s is a signed sum of rotations), its own RNG, its own transform code.
+// binary, so a*s is a signed sum of rotations), its own transform code, and ChaCha20 randomness
+// (chacha.h) keyed from the OS entropy source unless a caller passes a non-zero seed for a
+// reproducible run (tests, benchmarks).
 //
 // Produces exactly the structures the reference's CloudKey holds (cloudkey/cloudkey.go:16-21),
 // flattened as documented in include/tfhe_b200.h.
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
 
 #include "../../include/tfhe_b200.h"
+#include "chacha.h"
 
 namespace {
 
 typedef uint32_t Torus;
 
-// counter-based generator: every (seed, stream, index) triple gives an independent 64-bit word,
-// so results do not depend on the number of worker threads.
+// ChaCha20 streams (chacha.h): stream (domain, id) under the call's 256-bit key; results do not depend on the number of
+// worker threads.  Masks and noise of one ciphertext come from different domains.
 struct Stream {
-  uint64_t key, ctr = 0;
-  Stream(uint64_t seed, uint64_t stream) : key(mix(seed ^ mix(stream + 0x632BE59BD9B4E019ull))) {}
-  static uint64_t mix(uint64_t z) {
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+  tfhe::RngKey key;
+  uint32_t dom;
+  uint64_t id;
+  uint32_t buf[16], ctr = 0;
+  int pos = 16;
+  Stream(const tfhe::RngKey& k, uint32_t domain, uint64_t stream_id) : key(k), dom(domain), id(stream_id) {}
+  uint32_t u32() {
+    if (pos == 16) { tfhe::chacha20_block(key, ctr++, dom, (uint32_t)id, (uint32_t)(id >> 32), buf); pos = 0; }
+    return buf[pos++];
   }
-  uint64_t u64() { return mix(key + 0xD1342543DE82EF95ull * (++ctr)); }
-  uint32_t u32() { return (uint32_t)(u64() >> 32); }
-  double unit() { return ((u64() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+  double unit() { const uint32_t hi = u32(), lo = u32(); return tfhe::rng_unit(hi, lo); }
   double gauss() {  // Box-Muller, one value per call
     const double u = unit(), v = unit();
     return std::sqrt(-2.0 * std::log(u)) * std::cos(6.283185307179586476925286766559 * v);
   }
 };
+tfhe::RngKey call_key(uint64_t seed) {  // seed == 0: OS entropy (the default of the Python mirror); else reproducible
+  tfhe::RngKey k;
+  if (!tfhe::rng_make_key(seed, &k)) { std::fprintf(stderr, "tfhe_b200_client: no entropy source\n"); std::abort(); }
+  return k;
+}
 
 // real number -> torus, utils.F64ToTorus semantics (utils/utils.go:11-14): frac(d) * 2^32, truncated
 Torus to_torus(double d) {
   double f = std::fmod(d, 1.0) * 4294967296.0;
   return (Torus)(uint64_t)(int64_t)f;
 }
-Torus noisy(double mu, double sigma, Stream& rng) { return to_torus(mu) + to_torus(rng.gauss() * sigma); }
+Torus noisy(double mu, double sigma, Stream& noise) { return to_torus(mu) + to_torus(noise.gauss() * sigma); }
 
-void lwe_encrypt(const tfhe_params& P, double mu, double sigma, const Torus* s0, Stream& rng, Torus* out) {
+void lwe_encrypt(const tfhe_params& P, double mu, double sigma, const Torus* s0, Stream& mask, Stream& noise, Torus* out) {
   Torus dot = 0;
   for (int i = 0; i < P.n; i++) {
-    out[i] = rng.u32();
+    out[i] = mask.u32();
     dot += out[i] * s0[i];
   }
-  out[P.n] = dot + noisy(mu, sigma, rng);
+  out[P.n] = dot + noisy(mu, sigma, noise);
 }
 
 // (a * s) in Z[X]/(X^N+1) for binary s, exact mod 2^32
@@ -117,19 +127,30 @@ template <class F> void run_parallel(int count, int threads, F f) {
 
 extern "C" {
 
+// The ChaCha20 block function of chacha.h (shared with the device key generator), exposed for the RFC 8439 known-answer test.
+void tfhe_client_chacha20_block(const uint32_t key[8], uint32_t counter, const uint32_t nonce[3], uint32_t out[16]) {
+  tfhe::RngKey k;
+  std::memcpy(k.k, key, sizeof k.k);
+  uint32_t o[16];
+  tfhe::chacha20_block(k, counter, nonce[0], nonce[1], nonce[2], o);
+  std::memcpy(out, o, sizeof o);
+}
+
 // key.NewSecretKey (key/key.go:16-45): uniform binary keys of length n and N.
 void tfhe_client_secret_key(const tfhe_params* P, uint64_t seed, uint32_t* key_lv0, uint32_t* key_lv1) {
-  Stream a(seed, 1), b(seed, 2);
-  for (int i = 0; i < P->n; i++) key_lv0[i] = (uint32_t)(a.u64() >> 63);
-  for (int i = 0; i < P->N; i++) key_lv1[i] = (uint32_t)(b.u64() >> 63);
+  const tfhe::RngKey k = call_key(seed);
+  Stream a(k, tfhe::RNG_SK_LV0, 0), b(k, tfhe::RNG_SK_LV1, 0);
+  for (int i = 0; i < P->n; i++) key_lv0[i] = a.u32() >> 31;
+  for (int i = 0; i < P->N; i++) key_lv1[i] = b.u32() >> 31;
 }
 
 // tlwe.EncryptBool (tlwe/tlwe.go:54-62): mu = +-1/8.  count ciphertexts, ciphertext g uses stream (seed, g).
 void tfhe_client_encrypt_bool(const tfhe_params* P, double alpha, const uint32_t* key_lv0, uint64_t seed, int64_t count,
                               const uint8_t* bits, uint32_t* out) {
+  const tfhe::RngKey k = call_key(seed);
   for (int64_t g = 0; g < count; g++) {
-    Stream rng(seed, 0x10000000ull + (uint64_t)g);
-    lwe_encrypt(*P, bits[g] ? 0.125 : -0.125, alpha, key_lv0, rng, out + (size_t)g * (P->n + 1));
+    Stream mask(k, tfhe::RNG_ENC_MASK, (uint64_t)g), noise(k, tfhe::RNG_ENC_NOISE, (uint64_t)g);
+    lwe_encrypt(*P, bits[g] ? 0.125 : -0.125, alpha, key_lv0, mask, noise, out + (size_t)g * (P->n + 1));
   }
 }
 // tlwe.DecryptBool (tlwe/tlwe.go:65-74)
@@ -145,12 +166,13 @@ void tfhe_client_decrypt_bool(const tfhe_params* P, const uint32_t* key_lv0, int
 // tlwe.EncryptLWEMessage (tlwe/programmable_encrypt.go:12-27): mu = m / (2 * modulus)
 void tfhe_client_encrypt_message(const tfhe_params* P, double alpha, const uint32_t* key_lv0, uint64_t seed,
                                  int64_t count, const int32_t* msgs, int32_t modulus, uint32_t* out) {
+  const tfhe::RngKey k = call_key(seed);
   for (int64_t g = 0; g < count; g++) {
-    Stream rng(seed, 0x20000000ull + (uint64_t)g);
+    Stream mask(k, tfhe::RNG_ENC_MASK, (1ull << 40) + (uint64_t)g), noise(k, tfhe::RNG_ENC_NOISE, (1ull << 40) + (uint64_t)g);
     int m = msgs[g] % modulus;
     if (m < 0) m += modulus;
     const double mu = (double)m * (2147483648.0 / (double)modulus) / 4294967296.0;
-    lwe_encrypt(*P, mu, alpha, key_lv0, rng, out + (size_t)g * (P->n + 1));
+    lwe_encrypt(*P, mu, alpha, key_lv0, mask, noise, out + (size_t)g * (P->n + 1));
   }
 }
 // tlwe.DecryptLWEMessage (tlwe/programmable_encrypt.go:33-54)
@@ -193,6 +215,7 @@ void tfhe_client_cloud_key(const tfhe_params* Pp, double alpha_lv0, double alpha
                            const uint32_t* key_lv1, uint64_t seed, int threads, uint32_t* decomposition_offset,
                            uint32_t* testvec, uint32_t* ksk, double* bsk_fft) {
   const tfhe_params P = *Pp;
+  const tfhe::RngKey rk = call_key(seed);
   Torus off = 0;
   for (int l = 0; l < P.L; l++) off += (Torus)(1u << (P.bgbit - 1)) << (32 - (l + 1) * P.bgbit);
   *decomposition_offset = off;
@@ -204,9 +227,10 @@ void tfhe_client_cloud_key(const tfhe_params* Pp, double alpha_lv0, double alpha
         for (int k = 0; k < base; k++) {
           Torus* row = ksk + ((size_t)(i * P.iks_t + j) * base + k) * (P.n + 1);
           if (k == 0) { std::memset(row, 0, sizeof(Torus) * (P.n + 1)); continue; }
-          Stream rng(seed, 0x40000000ull + ((uint64_t)(i * P.iks_t + j) * base + k));
+          const uint64_t id = (uint64_t)(i * P.iks_t + j) * base + k;
+          Stream mask(rk, tfhe::RNG_KSK_MASK, id), noise(rk, tfhe::RNG_KSK_NOISE, id);
           const double mu = (double)k * (double)key_lv1[i] / (double)(1ull << ((j + 1) * P.basebit));
-          lwe_encrypt(P, mu, alpha_lv0, key_lv0, rng, row);
+          lwe_encrypt(P, mu, alpha_lv0, key_lv0, mask, noise, row);
         }
     });
   if (bsk_fft) {
@@ -215,10 +239,11 @@ void tfhe_client_cloud_key(const tfhe_params* Pp, double alpha_lv0, double alpha
       const int N = P.N;
       std::vector<Torus> A(N), B(N), as(N);
       for (int r = 0; r < 2 * P.L; r++) {  // TRGSW row r: TRLWE encryption of zero plus the gadget term
-        Stream rng(seed, 0x80000000ull + (uint64_t)i * 64 + r);
-        for (int k = 0; k < N; k++) A[k] = rng.u32();
+        const uint64_t id = (uint64_t)i * 2 * P.L + r;
+        Stream mask(rk, tfhe::RNG_BSK_MASK, id), noise(rk, tfhe::RNG_BSK_NOISE, id);
+        for (int k = 0; k < N; k++) A[k] = mask.u32();
         ring_mul_binary(A.data(), key_lv1, N, as.data());
-        for (int k = 0; k < N; k++) B[k] = as[k] + noisy(0.0, alpha_lv1, rng);
+        for (int k = 0; k < N; k++) B[k] = as[k] + noisy(0.0, alpha_lv1, noise);
         const int lvl = r % P.L;
         const Torus g = key_lv0[i] * ((Torus)1u << (32 - (lvl + 1) * P.bgbit));  // s_i / Bg^(lvl+1)
         if (r < P.L) A[0] += g; else B[0] += g;

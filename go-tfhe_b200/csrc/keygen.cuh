@@ -10,33 +10,24 @@
 //   utils.F64ToTorus / GaussianF64  utils/utils.go:11-49  (frac(d) * 2^32 truncated; mu and noise converted separately)
 //
 // The reference draws from unseeded math/rand, so there is nothing to match bit for bit: the outputs here follow the
-// same distributions (uniform masks, N(0, alpha^2) noise truncated to the torus the same way) from a counter-based
-// generator, one independent stream per ciphertext, so a key depends only on (secret key, seed).  Both kernels write
-// the REFERENCE layouts (FourierPoly groups of 4 re + 4 im; rows of n+1 words), i.e. exactly the CloudKey fields a Go
-// caller holds; the engine then ingests them through the same tfhe_ctx_load_cloudkey_device path as an uploaded key.
+// same distributions (uniform masks, N(0, alpha^2) noise truncated to the torus the same way).  Randomness is ChaCha20
+// (chacha.h) under a 256-bit key taken from the OS entropy source by the host (or expanded from a caller's seed for
+// reproducible tests), one stream per ciphertext and SEPARATE domains for the public masks and the secret noise.  Both
+// kernels write the REFERENCE layouts (FourierPoly groups of 4 re + 4 im; rows of n+1 words), i.e. exactly the CloudKey
+// fields a Go caller holds; the engine then ingests them through the same tfhe_ctx_load_cloudkey_device path as an
+// uploaded key.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "blind_rotate.cuh"
+#include "chacha.h"
 
 namespace tfhe {
 
-__host__ __device__ __forceinline__ uint64_t kg_mix(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-// stream key of ciphertext `id` in domain `dom` (0 = key-switching rows, 1 = TRLWE rows of the bootstrapping key)
-__host__ __device__ __forceinline__ uint64_t kg_stream(uint64_t seed, uint64_t dom, uint64_t id) {
-  return kg_mix(seed ^ kg_mix(2 * id + dom + 0x632BE59BD9B4E019ull));
-}
-__device__ __forceinline__ uint64_t kg_u64(uint64_t key, uint64_t idx) { return kg_mix(key + 0xD1342543DE82EF95ull * (idx + 1)); }
-__device__ __forceinline__ double kg_unit(uint64_t w) { return (double)((w >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
-// standard normal, Box-Muller on words (2 idx, 2 idx + 1) of the stream
-__device__ __forceinline__ double kg_gauss(uint64_t key, uint64_t idx) {
-  const double u = kg_unit(kg_u64(key, 2 * idx)), v = kg_unit(kg_u64(key, 2 * idx + 1));
+// standard normal from four stream words (Box-Muller)
+__device__ __forceinline__ double kg_gauss4(const uint32_t* w) {
+  const double u = rng_unit(w[0], w[1]), v = rng_unit(w[2], w[3]);
   return sqrt(-2.0 * log(u)) * cospi(2.0 * v);
 }
 // utils.F64ToTorus (utils/utils.go:11-14): Torus(int64(math.Mod(d, 1.0) * 2^32))
@@ -46,10 +37,9 @@ __device__ __forceinline__ uint32_t kg_to_torus(double d) {
 }
 
 // Key-switching key, reference layout [N*t*base][n+1].  grid = rows, block = 128.
-// Words [n + 1 ...) of the mask stream are the noise words, so mask and noise never share a counter.
 __global__ void __launch_bounds__(128) keygen_ksk_kernel(uint32_t* __restrict__ ksk, const uint32_t* __restrict__ s0,
                                                          const uint32_t* __restrict__ s1, int n, int basebit, int t,
-                                                         double alpha, uint64_t seed) {
+                                                         double alpha, const RngKey key) {
   __shared__ uint32_t red[4];
   const size_t row = blockIdx.x;
   uint32_t* dst = ksk + row * (size_t)(n + 1);
@@ -61,12 +51,15 @@ __global__ void __launch_bounds__(128) keygen_ksk_kernel(uint32_t* __restrict__ 
   const size_t ij = row >> basebit;
   const int j = (int)(ij % t);
   const size_t i = ij / t;
-  const uint64_t key = kg_stream(seed, 0, row);
   uint32_t dot = 0;
-  for (int w = threadIdx.x; w < n; w += blockDim.x) {
-    const uint32_t a = (uint32_t)(kg_u64(key, w) >> 32);
-    dst[w] = a;
-    dot += a * s0[w];
+  for (int blk = threadIdx.x; blk * 16 < n; blk += blockDim.x) {  // mask: block blk of stream (KSK_MASK, row)
+    uint32_t w[16];
+    chacha20_block(key, (uint32_t)blk, RNG_KSK_MASK, (uint32_t)row, (uint32_t)(row >> 32), w);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const int p = blk * 16 + q;
+      if (p < n) { dst[p] = w[q]; dot += w[q] * s0[p]; }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
@@ -75,8 +68,9 @@ __global__ void __launch_bounds__(128) keygen_ksk_kernel(uint32_t* __restrict__ 
   if (threadIdx.x == 0) {
     const uint32_t inner = red[0] + red[1] + red[2] + red[3];
     const double mu = ((double)k * (double)s1[i]) / (double)(1ull << ((j + 1) * basebit));
-    const double z = kg_gauss(key, (uint64_t)n + 1);
-    dst[n] = inner + kg_to_torus(mu) + kg_to_torus(z * alpha);
+    uint32_t w[16];
+    chacha20_block(key, 0, RNG_KSK_NOISE, (uint32_t)row, (uint32_t)(row >> 32), w);
+    dst[n] = inner + kg_to_torus(mu) + kg_to_torus(kg_gauss4(w) * alpha);
   }
 }
 
@@ -86,7 +80,7 @@ struct KeygenBskArgs {
   const uint32_t* s1;        // [N]  ring key bits
   const double2* tw_tab;
   double alpha;
-  uint64_t seed;
+  RngKey key;
   int L, bgbit;
   Tw4 tw0;
 };
@@ -101,19 +95,25 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), 2) keygen_bsk_kernel(const 
   const size_t rowid = blockIdx.x;          // = i * 2L + r
   const int r = (int)(rowid % (2 * A.L));
   const size_t i = rowid / (2 * A.L);
+  uint32_t* rnd = reinterpret_cast<uint32_t*>(smem_raw + (size_t)br_nbuf(LOGN) * TFHE_BR_EXW * M * 16);  // [N] mask words
   Fft<LOGN - 1, false> fft;
   fft.init(ex, A.tw_tab, tau);
+  {  // mask polynomial: the N words of stream (BSK_MASK, row); thread tau draws block tau (T = N/16 threads)
+    uint32_t w[16];
+    chacha20_block(A.key, (uint32_t)tau, RNG_BSK_MASK, (uint32_t)rowid, (uint32_t)(rowid >> 32), w);
+#pragma unroll
+    for (int q = 0; q < 16; q++) rnd[16 * tau + q] = w[q];
+  }
   __syncthreads();
-  const uint64_t key = kg_stream(A.seed, 1, rowid);
 
-  // mask polynomial (words [0, N) of the stream) and the ring key, folded as ToFourierPoly does (int32 view)
+  // mask and ring key, folded as ToFourierPoly does (int32 view)
   uint32_t are[8], aim[8];
   double2 x[8], y[8];
 #pragma unroll
   for (int a = 0; a < 8; a++) {
     const int j = tau + T * a;
-    are[a] = (uint32_t)(kg_u64(key, j) >> 32);
-    aim[a] = (uint32_t)(kg_u64(key, j + M) >> 32);
+    are[a] = rnd[j];
+    aim[a] = rnd[j + M];
     x[a] = make_double2((double)(int32_t)are[a], (double)(int32_t)aim[a]);
     y[a] = make_double2((double)(int32_t)A.s1[j], (double)(int32_t)A.s1[j + M]);
   }
@@ -131,12 +131,23 @@ __global__ void __launch_bounds__((1 << (LOGN - 4)), 2) keygen_bsk_kernel(const 
   const uint32_t bit = A.s0[i];
   const int l = (r < A.L) ? r : r - A.L;
   const uint32_t gadget = bit * (1u << (32 - (l + 1) * A.bgbit));
+  // noise: stream (BSK_NOISE, row); thread tau draws blocks 4 tau .. 4 tau + 3 = four words for each of its 16 coefficients
   uint32_t bre[8], bim[8];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint32_t w[16];
+    chacha20_block(A.key, (uint32_t)(4 * tau + q), RNG_BSK_NOISE, (uint32_t)rowid, (uint32_t)(rowid >> 32), w);
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      const int a = (4 * q + h) & 7;
+      const double z = kg_gauss4(w + 4 * h) * A.alpha;
+      if (4 * q + h < 8) bre[a] = to_torus<false>(y[a].x) + kg_to_torus(0.0) + kg_to_torus(z);
+      else bim[a] = to_torus<false>(y[a].y) + kg_to_torus(0.0) + kg_to_torus(z);
+    }
+  }
 #pragma unroll
   for (int a = 0; a < 8; a++) {
     const int j = tau + T * a;
-    bre[a] = to_torus<false>(y[a].x) + kg_to_torus(0.0) + kg_to_torus(kg_gauss(key, (uint64_t)N + j) * A.alpha);
-    bim[a] = to_torus<false>(y[a].y) + kg_to_torus(0.0) + kg_to_torus(kg_gauss(key, (uint64_t)N + j + M) * A.alpha);
     if (j == 0) {
       if (r < A.L) are[a] += gadget;
       else bre[a] += gadget;

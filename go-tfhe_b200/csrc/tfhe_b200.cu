@@ -962,6 +962,8 @@ int tfhe_ctx_generate_cloudkey(tfhe_ctx* g, const uint32_t* key_lv0, const uint3
   for (int i = 0; i < P.L; i++) offset += (uint32_t)(1u << (P.bgbit - 1)) * (uint32_t)(1u << (32 - (i + 1) * P.bgbit));
   std::vector<uint32_t> tv((size_t)2 * P.N, 0u);
   for (int i = 0; i < P.N; i++) tv[P.N + i] = 0x20000000u;
+  RngKey rkey;
+  if (!rng_make_key(seed, &rkey)) return fail(g, TFHE_ERR_STATE, "no entropy source (getrandom / /dev/urandom) for key generation");
   DevBuf s0, s1, sb, sk, st;
   cudaStream_t s = c->stream;
   cudaError_t e = s0.reserve((size_t)P.n * 4);
@@ -975,10 +977,10 @@ int tfhe_ctx_generate_cloudkey(tfhe_ctx* g, const uint32_t* key_lv0, const uint3
   if (e == cudaSuccess) {
     KeygenBskArgs a{};
     a.bsk_fft = sb.as<double>(); a.s0 = s0.as<uint32_t>(); a.s1 = s1.as<uint32_t>(); a.tw_tab = c->d_tw; a.alpha = alpha_lv1;
-    a.seed = seed; a.L = P.L; a.bgbit = P.bgbit; a.tw0 = c->tw0;
+    a.key = rkey; a.L = P.L; a.bgbit = P.bgbit; a.tw0 = c->tw0;
     const unsigned grid = (unsigned)((size_t)P.n * 2 * P.L);
     const int T = P.N / 16;
-    const size_t sm = (size_t)br_nbuf(c->logN) * TFHE_BR_EXW * (P.N / 2) * 16;
+    const size_t sm = (size_t)br_nbuf(c->logN) * TFHE_BR_EXW * (P.N / 2) * 16 + (size_t)P.N * 4 /* mask words */;
     switch (c->logN) {
       case 9: keygen_bsk_kernel<9><<<grid, T, sm, s>>>(a); break;
       case 10: keygen_bsk_kernel<10><<<grid, T, sm, s>>>(a); break;
@@ -989,7 +991,7 @@ int tfhe_ctx_generate_cloudkey(tfhe_ctx* g, const uint32_t* key_lv0, const uint3
   }
   if (e == cudaSuccess && with_ksk) {
     keygen_ksk_kernel<<<(unsigned)ksk_rows, 128, 0, s>>>(sk.as<uint32_t>(), s0.as<uint32_t>(), s1.as<uint32_t>(), P.n, P.basebit,
-                                                        P.iks_t, alpha_lv0, seed);
+                                                        P.iks_t, alpha_lv0, rkey);
     c->launches++;
     e = cudaGetLastError();
   }

@@ -8,6 +8,14 @@ import numpy as np
 from . import _native
 from .params import ParamSet
 
+
+def _seed(seed):
+    """None -> 0 (the C side then keys ChaCha20 from the OS entropy source); integers are reproducible test seeds."""
+    if seed is None:
+        return 0
+    seed = int(seed) & (2**64 - 1)
+    return seed if seed != 0 else 0x9E3779B97F4A7C15
+
 OPCODES = {"NAND": 0, "AND": 1, "OR": 2, "XOR": 3, "XNOR": 4, "NOR": 5, "ANDNY": 6, "ANDYN": 7, "ORNY": 8, "ORYN": 9,
            "MUX": 10, "NOT": 11, "COPY": 12}
 
@@ -93,7 +101,7 @@ class Context:
         self._ck(self.lib.tfhe_ctx_load_cloudkey(self.h, ctypes.c_uint32(offset), _ptr(bsk), _ptr(k), _ptr(tv)),
                  "tfhe_ctx_load_cloudkey")
 
-    def generate_cloudkey(self, key_lv0, key_lv1, seed=1, with_ksk=True, export=True):
+    def generate_cloudkey(self, key_lv0, key_lv1, seed=None, with_ksk=True, export=True):
         """cloudkey.NewCloudKey on the device (tfhe_ctx_generate_cloudkey).  Returns (offset, testvec, ksk, bsk_fft) in the
         reference layouts when export=True (ksk None without a key-switching key), else None; the key stays loaded."""
         P = self.P
@@ -103,7 +111,7 @@ class Context:
         tv = np.zeros((2, P.N), dtype=np.uint32) if export else None
         ksk = np.zeros((P.ksk_rows, P.n + 1), dtype=np.uint32) if (export and with_ksk) else None
         bsk = np.zeros((P.n, 2 * P.L, 2, P.N), dtype=np.float64) if export else None
-        self._ck(self.lib.tfhe_ctx_generate_cloudkey(self.h, _ptr(s0), _ptr(s1), P.alpha_lv0, P.alpha_lv1, int(seed) & (2**64 - 1),
+        self._ck(self.lib.tfhe_ctx_generate_cloudkey(self.h, _ptr(s0), _ptr(s1), P.alpha_lv0, P.alpha_lv1, _seed(seed),
                                                      1 if with_ksk else 0, ctypes.cast(ctypes.byref(off), ctypes.c_void_p),
                                                      _ptr(bsk), _ptr(ksk), _ptr(tv)), "tfhe_ctx_generate_cloudkey")
         return (off.value, tv, ksk, bsk) if export else None

@@ -5,16 +5,16 @@ import ctypes
 import numpy as np
 
 from . import _native
-from .key import _tp
+from .key import _tp, _seed
 
 
-def EncryptBool(bits, sk, seed=0, alpha=None):
+def EncryptBool(bits, sk, seed=None, alpha=None):
     """tlwe.EncryptBool (tlwe/tlwe.go:54-62) for every element of `bits`."""
     P = sk.P
     bits = np.ascontiguousarray(bits, dtype=np.uint8).ravel()
     out = np.zeros((len(bits), P.n + 1), dtype=np.uint32)
     _native.client().tfhe_client_encrypt_bool(ctypes.byref(_tp(P)), alpha if alpha is not None else P.alpha_lv0,
-                                              sk.KeyLv0.ctypes.data, seed, len(bits), bits.ctypes.data, out.ctypes.data)
+                                              sk.KeyLv0.ctypes.data, _seed(seed), len(bits), bits.ctypes.data, out.ctypes.data)
     return out
 
 
@@ -28,13 +28,13 @@ def DecryptBool(ct, sk):
     return bits
 
 
-def EncryptLWEMessage(msgs, messageModulus, sk, seed=0, alpha=None):
+def EncryptLWEMessage(msgs, messageModulus, sk, seed=None, alpha=None):
     """tlwe.EncryptLWEMessage (tlwe/programmable_encrypt.go:12-27)."""
     P = sk.P
     msgs = np.ascontiguousarray(msgs, dtype=np.int32).ravel()
     out = np.zeros((len(msgs), P.n + 1), dtype=np.uint32)
     _native.client().tfhe_client_encrypt_message(ctypes.byref(_tp(P)), alpha if alpha is not None else P.alpha_lv0,
-                                                 sk.KeyLv0.ctypes.data, seed, len(msgs), msgs.ctypes.data,
+                                                 sk.KeyLv0.ctypes.data, _seed(seed), len(msgs), msgs.ctypes.data,
                                                  int(messageModulus), out.ctypes.data)
     return out
 

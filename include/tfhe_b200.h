@@ -96,9 +96,12 @@ int tfhe_ctx_load_cloudkey(tfhe_ctx* ctx, uint32_t decomposition_offset, const d
  * (key.SecretKey.KeyLv0 [n], KeyLv1 [N], binary, as u32): genBootstrappingKey (:122-145: trgsw.EncryptTorus
  * trgsw/trgsw.go:32-58 over trlwe.EncryptF64 trlwe/trlwe.go:28-50, then NewTRGSWLv1FFT :72-82), genKeySwitchingKey
  * (:88-120, tlwe.EncryptF64 tlwe/tlwe.go:36-52 with alpha_lv0 = params.KSKAlpha()), genTestvec, genDecompositionOffset.
- * alpha_lv1 = params.BSKAlpha().  The reference seeds from unseeded math/rand; here the key is a deterministic
- * function of (secret key, seed).  The key is left loaded in ctx; the optional outputs receive the CloudKey fields in
- * the layouts of tfhe_ctx_load_cloudkey (any of them may be NULL; ksk_out requires with_ksk != 0). */
+ * alpha_lv1 = params.BSKAlpha().  Randomness is ChaCha20 under a 256-bit key, public masks and secret noise in separate
+ * streams: seed == 0 takes that key from the operating system's entropy source (getrandom) — the setting for real keys,
+ * like the reference's self-seeding math/rand but cryptographically strong; seed != 0 expands the seed into the key so
+ * that (secret key, seed) -> cloud key is reproducible (tests, benchmarks; 64 bits of entropy only).  The key is left
+ * loaded in ctx; the optional outputs receive the CloudKey fields in the layouts of tfhe_ctx_load_cloudkey (any of them
+ * may be NULL; ksk_out requires with_ksk != 0).  The secret key is only read by this call and never stored. */
 int tfhe_ctx_generate_cloudkey(tfhe_ctx* ctx, const uint32_t* key_lv0, const uint32_t* key_lv1, double alpha_lv0,
                                double alpha_lv1, uint64_t seed, int with_ksk, uint32_t* decomposition_offset_out,
                                double* bsk_fft_out, uint32_t* ksk_out, uint32_t* testvec_out);

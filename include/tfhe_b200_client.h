@@ -13,6 +13,10 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* Randomness: every `seed` below selects the ChaCha20 key of that call — 0 = 256 bits from the OS entropy source
+ * (what a real client uses; the Python mirror's default), non-zero = reproducible expansion of the seed (tests). */
+/* ChaCha20 block function (RFC 8439) used by this library and by the device key generator; for known-answer tests */
+void tfhe_client_chacha20_block(const uint32_t key[8], uint32_t counter, const uint32_t nonce[3], uint32_t out[16]);
 /* key.NewSecretKey, key/key.go:16-45 */
 void tfhe_client_secret_key(const tfhe_params* P, uint64_t seed, uint32_t* key_lv0, uint32_t* key_lv1);
 /* tlwe.EncryptBool / DecryptBool, tlwe/tlwe.go:54-74 */

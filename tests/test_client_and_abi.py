@@ -160,3 +160,40 @@ def test_wire_format_round_trip_and_rejects_corruption(T):
         T.wire.loads_cloud_key(blob, T.params.get("128"))
     with pytest.raises(ValueError):
         T.wire.loads_secret_key(blob, P)
+
+
+def test_chacha20_block_matches_rfc8439(T):
+    """The generator behind key generation and encryption (csrc/chacha.h, shared by client.cpp and the device keygen) is
+    the RFC 8439 block function: section 2.3.2 known-answer vector."""
+    key = np.frombuffer(bytes(range(32)), dtype="<u4").copy()
+    nonce = np.frombuffer(bytes([0, 0, 0, 9, 0, 0, 0, 0x4A, 0, 0, 0, 0]), dtype="<u4").copy()
+    out = np.zeros(16, dtype=np.uint32)
+    T._native.client().tfhe_client_chacha20_block(key.ctypes.data, 1, nonce.ctypes.data, out.ctypes.data)
+    want = [0xe4e7f110, 0x15593bd1, 0x1fdd0f50, 0xc47120a3, 0xc7f4d1c7, 0x0368c033, 0x9aaa2204, 0x4e6cd4c3,
+            0x466482d2, 0x09aa9f07, 0x05d7c214, 0xa2028bd9, 0xd19c12b5, 0xb94e16de, 0xe883d0cb, 0x4e3c50a2]
+    assert [int(v) for v in out] == want
+
+
+def test_default_randomness_is_fresh_and_seeds_reproduce(T):
+    """defaults must not be constants.  Without a seed every key and every encryption is fresh (OS
+    entropy -> ChaCha20 key): two default secret keys differ, two default encryptions of the same bits share neither
+    mask nor noise.  With a seed everything is reproducible, and masks and noise come from separate streams."""
+    P = T.params.get("80")
+    k1, k2 = T.key.NewSecretKey(P), T.key.NewSecretKey(P)
+    assert not np.array_equal(k1.KeyLv0, k2.KeyLv0) and not np.array_equal(k1.KeyLv1, k2.KeyLv1)
+    assert set(np.unique(k1.KeyLv0)) <= {0, 1} and 0.35 < k1.KeyLv1.mean() < 0.65
+    bits = np.ones(64, dtype=np.uint8)
+    c1, c2 = T.tlwe.EncryptBool(bits, k1), T.tlwe.EncryptBool(bits, k1)
+    assert not np.array_equal(c1[:, :-1], c2[:, :-1])          # masks differ
+    ph = lambda c: (c[:, -1].astype(np.int64) - (c[:, :-1].astype(np.int64) * k1.KeyLv0).sum(1)) % (1 << 32)
+    assert not np.array_equal(ph(c1), ph(c2))                   # noise differs
+    assert list(T.tlwe.DecryptBool(c1, k1)) == [1] * 64 and list(T.tlwe.DecryptBool(c2, k1)) == [1] * 64
+    s1, s2 = T.key.NewSecretKey(P, 7), T.key.NewSecretKey(P, 7)
+    assert np.array_equal(s1.KeyLv0, s2.KeyLv0)
+    assert np.array_equal(T.tlwe.EncryptBool(bits, s1, 3), T.tlwe.EncryptBool(bits, s1, 3))
+    assert not np.array_equal(T.tlwe.EncryptBool(bits, s1, 3), T.tlwe.EncryptBool(bits, s1, 4))
+    # noise of the default path has the parameter set's standard deviation (alpha * 2^32) and zero mean
+    big = T.tlwe.EncryptBool(np.ones(4000, dtype=np.uint8), k1)
+    err = ((ph(big) - (1 << 29) + (1 << 31)) % (1 << 32)) - (1 << 31)
+    sigma = P.alpha_lv0 * 2.0 ** 32
+    assert abs(err.mean()) < 5 * sigma / np.sqrt(4000) and 0.9 * sigma < err.std() < 1.1 * sigma
