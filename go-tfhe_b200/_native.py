@@ -13,6 +13,10 @@ class GateDesc(ctypes.Structure):
                 ("out", ctypes.c_int32)]
 
 
+class WireSection(ctypes.Structure):
+    _fields_ = [("tag", ctypes.c_char * 4), ("dtype", ctypes.c_uint32), ("count", ctypes.c_uint64), ("data", ctypes.c_void_p)]
+
+
 class TfheParams(ctypes.Structure):
     _fields_ = [("n", ctypes.c_int32), ("N", ctypes.c_int32), ("L", ctypes.c_int32), ("bgbit", ctypes.c_int32),
                 ("basebit", ctypes.c_int32), ("iks_t", ctypes.c_int32)]
@@ -26,7 +30,7 @@ ENGINE_SYMBOLS = [
 ]
 CLIENT_SYMBOLS = [
     "tfhe_client_secret_key", "tfhe_client_encrypt_bool", "tfhe_client_decrypt_bool", "tfhe_client_encrypt_message",
-    "tfhe_client_decrypt_message", "tfhe_client_gen_lut", "tfhe_client_cloud_key", "tfhe_client_chacha20_block",
+    "tfhe_client_decrypt_message", "tfhe_client_gen_lut", "tfhe_client_cloud_key", "tfhe_client_chacha20_block", "tfhe_wire_pack", "tfhe_wire_unpack",
 ]
 
 _engine = None
@@ -101,5 +105,10 @@ def client():
         lib.tfhe_client_chacha20_block.argtypes = [vp, ctypes.c_uint32, vp, vp]
         for s in CLIENT_SYMBOLS:
             getattr(lib, s).restype = None
+        lib.tfhe_wire_pack.argtypes = [ctypes.c_uint32, PP, ctypes.POINTER(WireSection), ctypes.c_uint32, vp, i64]
+        lib.tfhe_wire_pack.restype = i64
+        lib.tfhe_wire_unpack.argtypes = [vp, i64, ctypes.POINTER(ctypes.c_uint32), PP, ctypes.POINTER(WireSection),
+                                         ctypes.POINTER(ctypes.c_uint32)]
+        lib.tfhe_wire_unpack.restype = ctypes.c_int
         _client = lib
     return _client

@@ -44,7 +44,8 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed")
         with open(os.path.join(LIBDIR, "ptxas_info.txt"), "w") as f:
             f.write(res.stderr)
-    cl_src = [os.path.join(CSRC, "client.cpp"), os.path.join(inc, "tfhe_b200.h")]
+    cl_src = [os.path.join(CSRC, "client.cpp"), os.path.join(CSRC, "chacha.h"), os.path.join(inc, "tfhe_b200.h"),
+              os.path.join(inc, "tfhe_b200_client.h")]
     if force or _stale(CLIENT, cl_src):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", CLIENT,
                                os.path.join(CSRC, "client.cpp")])

@@ -18,7 +18,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/tfhe_b200.h"
+#include "../../include/tfhe_b200_client.h"
 #include "chacha.h"
 
 namespace {
@@ -126,6 +126,100 @@ template <class F> void run_parallel(int count, int threads, F f) {
 }  // namespace
 
 extern "C" {
+
+// ---- TFHB wire format (go-tfhe_b200/wire.py, go/tfheb200/wire.go hold the same format) -----------------------------
+//   "TFHB" | version u32 (2) | kind u32 | params 6 x i32 | nsect u32 | sections | crc u64
+//   section: tag (4 ascii bytes, space padded) | dtype u32 (0 = u32, 1 = f64) | count u64 | count little-endian values
+//   crc: CRC-32 (IEEE 802.3, the zlib / Go hash/crc32 polynomial) of every byte before it, zero-extended to 64 bits
+static uint32_t wire_crc32(const unsigned char* p, size_t n) {
+  static uint32_t table[256];
+  static bool init = false;
+  if (!init) {
+    for (uint32_t i = 0; i < 256; i++) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      table[i] = c;
+    }
+    init = true;
+  }
+  uint32_t c = 0xFFFFFFFFu;
+  for (size_t i = 0; i < n; i++) c = table[(c ^ p[i]) & 0xFF] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+static const uint32_t kWireVersion = 2;
+
+// Serialises `nsect` sections.  out == NULL: returns the size needed.  Else writes at most out_cap bytes and returns the
+// size written, or -1 if out_cap is too small / an argument is invalid.  Little-endian hosts only (x86-64, aarch64).
+int64_t tfhe_wire_pack(uint32_t kind, const tfhe_params* P, const tfhe_wire_section* sections, uint32_t nsect, void* out,
+                       int64_t out_cap) {
+  if (!P || (nsect && !sections)) return -1;
+  size_t need = 4 + 4 + 4 + 24 + 4 + 8;
+  for (uint32_t i = 0; i < nsect; i++) {
+    if (sections[i].dtype > 1 || (sections[i].count && !sections[i].data)) return -1;
+    need += 16 + (size_t)sections[i].count * (sections[i].dtype ? 8 : 4);
+  }
+  if (!out) return (int64_t)need;
+  if ((size_t)out_cap < need) return -1;
+  unsigned char* w = static_cast<unsigned char*>(out);
+  size_t off = 0;
+  auto put = [&](const void* src, size_t n) { std::memcpy(w + off, src, n); off += n; };
+  put("TFHB", 4);
+  put(&kWireVersion, 4);
+  put(&kind, 4);
+  const int32_t pv[6] = {P->n, P->N, P->L, P->bgbit, P->basebit, P->iks_t};
+  put(pv, 24);
+  put(&nsect, 4);
+  for (uint32_t i = 0; i < nsect; i++) {
+    put(sections[i].tag, 4);
+    put(&sections[i].dtype, 4);
+    put(&sections[i].count, 8);
+    put(sections[i].data, (size_t)sections[i].count * (sections[i].dtype ? 8 : 4));
+  }
+  const uint64_t crc = wire_crc32(w, off);
+  put(&crc, 8);
+  return (int64_t)off;
+}
+
+// Parses a blob: checks magic, version and checksum, fills kind / params and up to *nsect section descriptors whose
+// `data` pointers point INTO the blob (valid while it is).  On return *nsect is the number of sections in the blob.
+// Returns 0, or -1 malformed / truncated, -2 bad checksum, -3 unsupported version, -4 more sections than capacity.
+int tfhe_wire_unpack(const void* blob, int64_t size, uint32_t* kind, tfhe_params* P, tfhe_wire_section* sections,
+                     uint32_t* nsect) {
+  if (!blob || !kind || !P || !nsect || size < 48) return -1;
+  const unsigned char* r = static_cast<const unsigned char*>(blob);
+  if (std::memcmp(r, "TFHB", 4) != 0) return -1;
+  uint32_t version;
+  std::memcpy(&version, r + 4, 4);
+  if (version != kWireVersion) return -3;
+  uint64_t crc;
+  std::memcpy(&crc, r + size - 8, 8);
+  if (crc != (uint64_t)wire_crc32(r, (size_t)size - 8)) return -2;
+  std::memcpy(kind, r + 8, 4);
+  int32_t pv[6];
+  std::memcpy(pv, r + 12, 24);
+  P->n = pv[0]; P->N = pv[1]; P->L = pv[2]; P->bgbit = pv[3]; P->basebit = pv[4]; P->iks_t = pv[5];
+  uint32_t ns;
+  std::memcpy(&ns, r + 36, 4);
+  const uint32_t cap = *nsect;
+  *nsect = ns;
+  size_t off = 40;
+  for (uint32_t i = 0; i < ns; i++) {
+    if (off + 16 > (size_t)size - 8) return -1;
+    tfhe_wire_section sec;
+    std::memcpy(sec.tag, r + off, 4);
+    std::memcpy(&sec.dtype, r + off + 4, 4);
+    std::memcpy(&sec.count, r + off + 8, 8);
+    off += 16;
+    if (sec.dtype > 1) return -1;
+    const size_t bytes = (size_t)sec.count * (sec.dtype ? 8 : 4);
+    if (bytes > (size_t)size - 8 - off) return -1;
+    sec.data = r + off;
+    off += bytes;
+    if (i < cap && sections) sections[i] = sec;
+  }
+  if (off != (size_t)size - 8) return -1;
+  return ns > cap ? -4 : 0;
+}
 
 // The ChaCha20 block function of chacha.h (shared with the device key generator), exposed for the RFC 8439 known-answer test.
 void tfhe_client_chacha20_block(const uint32_t key[8], uint32_t counter, const uint32_t nonce[3], uint32_t out[16]) {

@@ -13,6 +13,20 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+/* --- TFHB wire format: keys and ciphertext batches as flat files (the reference has no serialisation at all; its
+ * "format" is the Go structs key.SecretKey key/key.go:10-13 and cloudkey.CloudKey cloudkey/cloudkey.go:16-21).  The same
+ * format is written by go/tfheb200/wire.go (so that a real Go run can ship keys and golden vectors) and by
+ * go-tfhe_b200/wire.py.  Layout: "TFHB", version u32 = 2, kind u32, params 6 x i32, nsect u32, sections (tag[4], dtype
+ * u32: 0 = u32 / 1 = f64, count u64, data), CRC-32 (IEEE) of everything before it as u64.  Kinds: 1 SecretKey (lv0, lv1),
+ * 2 CloudKey (offs, tvec, bsk, [ksk]), 3 ciphertext batch (ct), 4 TRLWE / LUT batch (trlw), 5 named vector bundle. */
+typedef struct { char tag[4]; uint32_t dtype; uint64_t count; const void* data; } tfhe_wire_section;
+/* out == NULL: size needed; else bytes written, or -1 (buffer too small / bad argument) */
+int64_t tfhe_wire_pack(uint32_t kind, const tfhe_params* P, const tfhe_wire_section* sections, uint32_t nsect, void* out,
+                       int64_t out_cap);
+/* 0 ok (section data pointers point into blob); -1 malformed, -2 checksum, -3 version, -4 *nsect (capacity) too small;
+ * on return *nsect = sections in the blob */
+int tfhe_wire_unpack(const void* blob, int64_t size, uint32_t* kind, tfhe_params* P, tfhe_wire_section* sections,
+                     uint32_t* nsect);
 /* Randomness: every `seed` below selects the ChaCha20 key of that call — 0 = 256 bits from the OS entropy source
  * (what a real client uses; the Python mirror's default), non-zero = reproducible expansion of the seed (tests). */
 /* ChaCha20 block function (RFC 8439) used by this library and by the device key generator; for known-answer tests */

@@ -197,3 +197,30 @@ def test_default_randomness_is_fresh_and_seeds_reproduce(T):
     err = ((ph(big) - (1 << 29) + (1 << 31)) % (1 << 32)) - (1 << 31)
     sigma = P.alpha_lv0 * 2.0 ** 32
     assert abs(err.mean()) < 5 * sigma / np.sqrt(4000) and 0.9 * sigma < err.std() < 1.1 * sigma
+
+
+def test_wire_format_c_and_python_writers_agree(T):
+    """The C reader/writer of libtfhe_b200_client (tfhe_wire_pack / tfhe_wire_unpack — what a cgo or C++ caller links) and
+    go-tfhe_b200/wire.py hold the same format: identical bytes out, each reads the other's, corruption anywhere (a swap of
+    two words included: the checksum is a real CRC-32) is rejected by both."""
+    P = T.params.get("80")
+    sk = T.key.NewSecretKey(P, 5)
+    rng = np.random.default_rng(0)
+    sections = [("lv0", sk.KeyLv0), ("lv1", sk.KeyLv1), ("bsk", rng.standard_normal(40)), ("x", np.zeros(0, dtype=np.uint32))]
+    py = T.wire._pack(T.wire.KIND_BUNDLE, P, sections)
+    c = T.wire.c_pack(T.wire.KIND_BUNDLE, P, sections)
+    assert py == c
+    kind, pvals, got = T.wire.c_unpack(py)
+    assert kind == T.wire.KIND_BUNDLE and pvals == (P.n, P.N, P.L, P.BGBIT, P.BASEBIT, P.IKS_T)
+    assert np.array_equal(got["lv0"], sk.KeyLv0) and np.array_equal(got["bsk"], sections[2][1]) and got["x"].size == 0
+    assert np.array_equal(T.wire.loads_secret_key(T.wire.c_pack(T.wire.KIND_SECRET, P, sections[:2]), P).KeyLv1, sk.KeyLv1)
+    i = int(np.flatnonzero(sk.KeyLv0[:-1] != sk.KeyLv0[1:])[0])  # two adjacent, different key words exchanged
+    o = 56 + 4 * i                                               # 40 header bytes + 16 section-header bytes
+    swapped = bytearray(py)
+    swapped[o:o + 4], swapped[o + 4:o + 8] = py[o + 4:o + 8], py[o:o + 4]
+    assert bytes(swapped) != py
+    for bad in (bytes(swapped), py[:-9] + py[-8:], py[:100] + bytes([py[100] ^ 1]) + py[101:]):
+        with pytest.raises(ValueError):
+            T.wire.c_unpack(bad)
+        with pytest.raises(ValueError):
+            T.wire.loads_bundle(bad)
