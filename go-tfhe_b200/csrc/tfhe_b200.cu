@@ -723,6 +723,13 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
     c->br_variant = !strcmp(sel, "tma") ? 1 : !strcmp(sel, "tex") ? 2 : !strcmp(sel, "w16") ? 3 : !strcmp(sel, "tmem") ? 4 : !strcmp(sel, "tmex") ? 5 : !strcmp(sel, "tmex+tma") ? 6 : !strcmp(sel, "tms") ? 7 : !strcmp(sel, "mg") ? 8 : !strcmp(sel, "lat2") ? 11 : !strcmp(sel, "cl") ? 13 : c->br_variant;
 #endif
   if (c->br_variant == 10) { c->br_variant = 0; c->br_auto_lat = false; }
+  {  // key generation: exchange buffers + the row's mask words (56 KiB at N = 2048: above the 48 KiB default)
+    const int kg_smem = (int)((size_t)br_nbuf(c->logN) * TFHE_BR_EXW * (P.N / 2) * 16 + (size_t)P.N * 4);
+    e = c->logN == 9 ? cudaFuncSetAttribute(keygen_bsk_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, kg_smem)
+      : c->logN == 10 ? cudaFuncSetAttribute(keygen_bsk_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, kg_smem)
+                      : cudaFuncSetAttribute(keygen_bsk_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, kg_smem);
+    if (e != cudaSuccess) return bail("cudaFuncSetAttribute(keygen_bsk)", e);
+  }
   if ((e = cudaFuncSetAttribute(V.cmux, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cmux_smem(P.N))) != cudaSuccess)
     return bail("cudaFuncSetAttribute(cmux)", e);
   if ((e = cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KSM_SMEM)) != cudaSuccess)

@@ -4,8 +4,9 @@
 // and scatters the results into freshly allocated reference types, so gates.* / evaluator.* keep
 // their signatures.  Errors become panics, matching the reference's convention.
 //
-// NOTE: this image has no Go toolchain; the file is reviewed by reading and mirrored line for line by
-// go-tfhe_b200/{cloudkey,evaluator,gates}.py, which the tests exercise against the same C ABI.
+// NOTE: the build image has no Go toolchain; the file is reviewed by reading and mirrored line for line by
+// go-tfhe_b200/{cloudkey,evaluator,gates}.py, which the tests exercise against the same C ABI.  INTEGRATION.md lists
+// what to run (go vet, the reference's own gate tests with -tags b200) the first time a toolchain is at hand.
 package tfheb200
 
 /*
@@ -48,20 +49,29 @@ const (
 	COPY
 )
 
-// Engine owns one tfhe_ctx (one GPU) with a cloud key resident on the device.
+// Engine owns one tfhe_ctx — by default a multi-device context over every visible GPU (tfhe_ctx_create_multi), so that
+// one gates.Batch* call fans out over the node the way trgsw.BatchBlindRotate fans out over goroutines — with a cloud
+// key resident on every device.
 type Engine struct {
-	mu  sync.Mutex // one call at a time per context
-	ctx *C.tfhe_ctx
-	n   int // TLWELv0.N
-	bigN int // TRGSWLv1.N
+	mu     sync.Mutex // one call at a time per context
+	ctx    *C.tfhe_ctx
+	n      int // TLWELv0.N
+	bigN   int // TRGSWLv1.N
+	hasKSK bool
+	kskID  **tlwe.TLWELv0 // identity of the key-switching key that is loaded (nil: none)
 }
 
+// Engines are cached per cloud key.  The maps hold strong references, so an engine (and its GPU memory) lives until
+// Release / ReleaseAll is called; there is deliberately no finalizer.
 var (
-	enginesMu sync.Mutex
-	engines   = map[*cloudkey.CloudKey]*Engine{}
+	enginesMu   sync.Mutex
+	engines     = map[*cloudkey.CloudKey]*Engine{}
+	partEngines = map[**trgsw.TRGSWLv1FFT]*Engine{}
+	// Devices selects the GPUs new engines use: nil = every visible GPU.
+	Devices []int
 )
 
-// For returns (creating and uploading on first use) the engine bound to ck on GPU 0.
+// For returns (creating and uploading on first use) the engine bound to ck.
 // gates.* call this, so user code keeps passing *cloudkey.CloudKey exactly as before.
 func For(ck *cloudkey.CloudKey) *Engine {
 	enginesMu.Lock()
@@ -69,43 +79,115 @@ func For(ck *cloudkey.CloudKey) *Engine {
 	if e, ok := engines[ck]; ok {
 		return e
 	}
-	e := New(ck, 0)
+	e := New(ck, Devices...)
 	engines[ck] = e
 	return e
 }
 
 // ForParts serves the evaluator.* entry points, which receive the pieces of a CloudKey instead of the struct
-// (evaluator/evaluator.go:139): engines are cached by the identity of the bootstrapping-key slice.
+// (evaluator/evaluator.go:139).  Engines are cached by the identity of the bootstrapping-key slice; the other pieces
+// are compared on every call and (re)uploaded when they differ from what the engine holds — an engine first created by
+// BlindRotateAssign (no key-switching key) gets its KSK the first time BootstrapAssign asks for one.
 func ForParts(bsk []*trgsw.TRGSWLv1FFT, ksk []*tlwe.TLWELv0, offset params.Torus, testvec *trlwe.TRLWELv1) *Engine {
+	if len(bsk) == 0 {
+		panic("tfheb200: empty bootstrapping key")
+	}
 	enginesMu.Lock()
 	defer enginesMu.Unlock()
-	key := &bsk[0]
-	if e, ok := partEngines[key]; ok {
-		return e
-	}
 	if testvec == nil {
 		testvec = trlwe.NewTRLWELv1()
 	}
-	e := New(&cloudkey.CloudKey{DecompositionOffset: offset, BlindRotateTestvec: testvec, KeySwitchingKey: ksk,
-		BootstrappingKey: bsk}, 0)
+	ck := &cloudkey.CloudKey{DecompositionOffset: offset, BlindRotateTestvec: testvec, KeySwitchingKey: ksk,
+		BootstrappingKey: bsk}
+	key := &bsk[0]
+	if e, ok := partEngines[key]; ok {
+		if len(ksk) > 0 && (!e.hasKSK || e.kskID != &ksk[0]) {
+			e.load(ck) // same BSK, new or first KSK: load the pair again (the engine never mixes keys)
+		}
+		return e
+	}
+	e := New(ck, Devices...)
 	partEngines[key] = e
 	return e
 }
 
-var partEngines = map[**trgsw.TRGSWLv1FFT]*Engine{}
-
-// New flattens ck (cloudkey/cloudkey.go:16-21) and uploads it to `device`.
-func New(ck *cloudkey.CloudKey, device int) *Engine {
-	g, l0 := params.GetTRGSWLv1(), params.GetTLWELv0()
-	p := C.tfhe_params{n: C.int32_t(l0.N), N: C.int32_t(g.N), L: C.int32_t(g.L), bgbit: C.int32_t(g.BGBIT),
-		basebit: C.int32_t(g.BASEBIT), iks_t: C.int32_t(g.IKS_T)}
-	var ctx *C.tfhe_ctx
-	if rc := C.tfhe_ctx_create(&p, C.int(device), &ctx); rc != 0 {
-		panic("tfhe_ctx_create: " + C.GoString(C.tfhe_last_error(nil)))
+// Release destroys the engine cached for ck (and its copies of the key on the GPUs).
+func Release(ck *cloudkey.CloudKey) {
+	enginesMu.Lock()
+	defer enginesMu.Unlock()
+	if e, ok := engines[ck]; ok {
+		delete(engines, ck)
+		e.Close()
 	}
-	e := &Engine{ctx: ctx, n: l0.N, bigN: g.N}
-	runtime.SetFinalizer(e, func(e *Engine) { C.tfhe_ctx_destroy(e.ctx) })
+	if len(ck.BootstrappingKey) > 0 {
+		if e, ok := partEngines[&ck.BootstrappingKey[0]]; ok {
+			delete(partEngines, &ck.BootstrappingKey[0])
+			e.Close()
+		}
+	}
+}
 
+// ReleaseAll destroys every cached engine.
+func ReleaseAll() {
+	enginesMu.Lock()
+	defer enginesMu.Unlock()
+	for k, e := range engines {
+		delete(engines, k)
+		e.Close()
+	}
+	for k, e := range partEngines {
+		delete(partEngines, k)
+		e.Close()
+	}
+}
+
+// Close frees the context; the Engine must not be used afterwards.
+func (e *Engine) Close() {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if e.ctx != nil {
+		C.tfhe_ctx_destroy(e.ctx)
+		e.ctx = nil
+	}
+}
+
+func curParams() (C.tfhe_params, int, int) {
+	g, l0 := params.GetTRGSWLv1(), params.GetTLWELv0()
+	return C.tfhe_params{n: C.int32_t(l0.N), N: C.int32_t(g.N), L: C.int32_t(g.L), bgbit: C.int32_t(g.BGBIT),
+		basebit: C.int32_t(g.BASEBIT), iks_t: C.int32_t(g.IKS_T)}, l0.N, g.N
+}
+
+func newEngine(devices []int) *Engine {
+	p, n, bigN := curParams()
+	var ctx *C.tfhe_ctx
+	var rc C.int
+	if len(devices) == 0 {
+		rc = C.tfhe_ctx_create_multi(&p, 0, nil, &ctx) // every visible GPU
+	} else {
+		devs := make([]C.int, len(devices))
+		for i, d := range devices {
+			devs[i] = C.int(d)
+		}
+		rc = C.tfhe_ctx_create_multi(&p, C.int(len(devs)), &devs[0], &ctx)
+	}
+	if rc != 0 {
+		panic("tfhe_ctx_create_multi: " + C.GoString(C.tfhe_last_error(nil)))
+	}
+	return &Engine{ctx: ctx, n: n, bigN: bigN}
+}
+
+// New flattens ck (cloudkey/cloudkey.go:16-21) and uploads it to `devices` (none given: every visible GPU).  The key
+// goes to the first device once and is replicated to the others by peer copies inside the library.
+func New(ck *cloudkey.CloudKey, devices ...int) *Engine {
+	e := newEngine(devices)
+	e.load(ck)
+	return e
+}
+
+// load flattens and uploads ck; a CloudKey without a KeySwitchingKey (cloudkey.NewCloudKeyNoKSK, or the pieces handed to
+// BlindRotateAssign) is uploaded with a NULL ksk: the engine then serves blind rotations only.
+func (e *Engine) load(ck *cloudkey.CloudKey) {
+	g, l0 := params.GetTRGSWLv1(), params.GetTLWELv0()
 	// BootstrappingKey []*TRGSWLv1FFT -> [n][2L][2][N] float64, reference FourierPoly layout untouched
 	bsk := make([]float64, 0, l0.N*2*g.L*2*g.N)
 	for _, row := range ck.BootstrappingKey {
@@ -115,35 +197,40 @@ func New(ck *cloudkey.CloudKey, device int) *Engine {
 		}
 	}
 	// KeySwitchingKey []*TLWELv0 (index base*t*i + base*j + k) -> [N*t*base][n+1] uint32
-	ksk := make([]uint32, 0, len(ck.KeySwitchingKey)*(l0.N+1))
-	for _, row := range ck.KeySwitchingKey {
-		ksk = appendTorus(ksk, row.P)
+	var pksk *C.uint32_t
+	var ksk []uint32
+	if len(ck.KeySwitchingKey) > 0 {
+		ksk = make([]uint32, 0, len(ck.KeySwitchingKey)*(l0.N+1))
+		for _, row := range ck.KeySwitchingKey {
+			ksk = appendTorus(ksk, row.P)
+		}
+		pksk = (*C.uint32_t)(&ksk[0])
 	}
 	tv := appendTorus(appendTorus(make([]uint32, 0, 2*g.N), ck.BlindRotateTestvec.A), ck.BlindRotateTestvec.B)
-	e.check(C.tfhe_ctx_load_cloudkey(ctx, C.uint32_t(ck.DecompositionOffset), (*C.double)(&bsk[0]),
-		(*C.uint32_t)(&ksk[0]), (*C.uint32_t)(&tv[0])), "tfhe_ctx_load_cloudkey")
-	return e
+	e.check(C.tfhe_ctx_load_cloudkey(e.ctx, C.uint32_t(ck.DecompositionOffset), (*C.double)(&bsk[0]), pksk,
+		(*C.uint32_t)(&tv[0])), "tfhe_ctx_load_cloudkey")
+	runtime.KeepAlive(ksk)
+	e.hasKSK = len(ck.KeySwitchingKey) > 0
+	e.kskID = nil
+	if e.hasKSK {
+		e.kskID = &ck.KeySwitchingKey[0]
+	}
 }
 
 // NewCloudKeyOnDevice is cloudkey.NewCloudKey (cloudkey/cloudkey.go:24-31) with the key material generated in GPU
 // memory (tfhe_ctx_generate_cloudkey): the returned CloudKey holds the same fields in the same formats as the Go
 // generator's, and the engine that made it is registered for it, so gates.* use it without a second upload.
-func NewCloudKeyOnDevice(keyLv0, keyLv1 []params.Torus, seed uint64, device int) *cloudkey.CloudKey {
+// seed == 0 (what production code passes) keys the generator from the operating system's entropy source; a non-zero
+// seed makes the key a reproducible function of (secret key, seed) for tests.  The secret key is read by this call only.
+func NewCloudKeyOnDevice(keyLv0, keyLv1 []params.Torus, seed uint64, devices ...int) *cloudkey.CloudKey {
 	g, l0 := params.GetTRGSWLv1(), params.GetTLWELv0()
-	p := C.tfhe_params{n: C.int32_t(l0.N), N: C.int32_t(g.N), L: C.int32_t(g.L), bgbit: C.int32_t(g.BGBIT),
-		basebit: C.int32_t(g.BASEBIT), iks_t: C.int32_t(g.IKS_T)}
-	var ctx *C.tfhe_ctx
-	if rc := C.tfhe_ctx_create(&p, C.int(device), &ctx); rc != 0 {
-		panic("tfhe_ctx_create: " + C.GoString(C.tfhe_last_error(nil)))
-	}
-	e := &Engine{ctx: ctx, n: l0.N, bigN: g.N}
-	runtime.SetFinalizer(e, func(e *Engine) { C.tfhe_ctx_destroy(e.ctx) })
+	e := newEngine(devices)
 	rows := g.N * g.IKS_T * (1 << g.BASEBIT)
 	bsk := make([]float64, l0.N*2*g.L*2*g.N)
 	ksk := make([]uint32, rows*(l0.N+1))
 	tv := make([]uint32, 2*g.N)
 	var off C.uint32_t
-	e.check(C.tfhe_ctx_generate_cloudkey(ctx, (*C.uint32_t)(unsafe.Pointer(&keyLv0[0])), (*C.uint32_t)(unsafe.Pointer(&keyLv1[0])),
+	e.check(C.tfhe_ctx_generate_cloudkey(e.ctx, (*C.uint32_t)(unsafe.Pointer(&keyLv0[0])), (*C.uint32_t)(unsafe.Pointer(&keyLv1[0])),
 		C.double(params.KSKAlpha()), C.double(params.BSKAlpha()), C.uint64_t(seed), 1, &off, (*C.double)(&bsk[0]),
 		(*C.uint32_t)(&ksk[0]), (*C.uint32_t)(&tv[0])), "tfhe_ctx_generate_cloudkey")
 	ck := &cloudkey.CloudKey{DecompositionOffset: params.Torus(off), BlindRotateTestvec: trlwe.NewTRLWELv1()}
@@ -168,11 +255,16 @@ func NewCloudKeyOnDevice(keyLv0, keyLv1 []params.Torus, seed uint64, device int)
 		}
 		ck.BootstrappingKey[i] = row
 	}
+	e.hasKSK = true
+	e.kskID = &ck.KeySwitchingKey[0]
 	enginesMu.Lock()
 	engines[ck] = e
 	enginesMu.Unlock()
 	return ck
 }
+
+// DeviceCount reports how many GPUs serve this engine.
+func (e *Engine) DeviceCount() int { return int(C.tfhe_ctx_device_count(e.ctx)) }
 
 func appendTorus(dst []uint32, src []params.Torus) []uint32 {
 	// params.Torus is uint32 (params/params.go:27): same memory layout

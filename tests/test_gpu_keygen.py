@@ -121,3 +121,21 @@ def test_generated_key_is_deterministic_in_seed(T, O):
         assert not np.array_equal(a.KeySwitchingKey, c.KeySwitchingKey)
     finally:
         a.close(); b.close(); c.close()
+
+
+def test_device_keygen_uint5_without_export(T):
+    """N = 2048: the key-generation kernel needs more than the default 48 KiB of dynamic shared memory (exchange buffers
+    + the row's ChaCha20 mask words); the 1.57 GiB key-switching key is generated, repacked and used without ever
+    leaving the device.  Decoded programmable bootstraps must be exact."""
+    P = T.params.get("uint5")
+    sk = T.key.NewSecretKey(P, 41)
+    ctx = T.Context(P, 0)
+    try:
+        ctx.generate_cloudkey(sk.KeyLv0, sk.KeyLv1, seed=42, with_ksk=True, export=False)
+        msgs = np.arange(32)
+        ct = T.tlwe.EncryptLWEMessage(msgs, 32, sk, 43)
+        lut = T.lut.NewGenerator(32, P).GenLookUpTable(lambda v: (v * 3 + 1) % 32).Poly.reshape(1, -1)
+        got = ctx.bootstrap_batch(ct, lut)
+        assert list(T.tlwe.DecryptLWEMessage(got, 32, sk)) == [(int(v) * 3 + 1) % 32 for v in msgs]
+    finally:
+        ctx.close()
