@@ -85,6 +85,9 @@ struct BrArgs {
   uint32_t offset;          // CloudKey.DecompositionOffset
   int out_mode;
   Tw4 tw0;                  // pass-0 twiddles (same for every thread; lives in the constant bank)
+  const int* lut_index;     // NULL, or [count] indices into luts (a small LUT table shared by many ciphertexts)
+  int ms_log2k;             // many-LUT bootstraps: the mod switch keeps multiples of 2^ms_log2k only (0 = reference)
+  int extract_k;            // out_mode 2: samples extracted at indices 0..extract_k-1 -> out [count][extract_k][N+1]
   // work distribution of the persistent throughput kernel (blind_rotate_kernel); ignored by the latency kernels
   long long count;          // gates in this launch
   int nchunks;              // work items per gate (1 = a whole gate per item)
@@ -452,6 +455,27 @@ struct Fft {
     }
   }
   __device__ __forceinline__ void forward(double2 (&x)[8], const Tw4& tw0) { forward(x, tw0, NoHook()); }
+  // same with a second hook after the barrier of the LAST exchange (N = 1024: h1 -> pass 1 -> h2 -> pass 2)
+  template <class Hook1, class Hook2>
+  __device__ __forceinline__ void forward_hooks(double2 (&x)[8], const Tw4& tw0, const Hook1& h1, const Hook2& h2) {
+    fwd_pass<0>(x, tw0);
+    if constexpr (G::NPASS == 3) {
+      exchange<0, 1>(x, h1); fwd_pass<1>(x, tw0);
+      exchange<1, 2>(x, h2); fwd_pass<2>(x, tw0);
+    } else {
+      forward_rest(x, tw0, h1);
+      h2();
+    }
+  }
+  template <class Hook>
+  __device__ __forceinline__ void forward_rest(double2 (&x)[8], const Tw4& tw0, const Hook& hook) {  // forward() minus pass 0
+    if constexpr (G::NPASS > 1) { exchange<0, 1>(x, hook); fwd_pass<1>(x, tw0); }
+    if constexpr (G::NPASS > 2) { exchange<1, 2>(x); fwd_pass<2>(x, tw0); }
+    if constexpr (G::NPASS > 3) {
+      if constexpr (SHFL_LAST) last_stage_fwd(x);
+      else { exchange<2, 3>(x); fwd_pass<3>(x, tw0); }
+    }
+  }
   // forward() split in two so that a caller can put long-latency loads in flight before the last register pass
   __device__ __forceinline__ void forward_head(double2 (&x)[8], const Tw4& tw0) {
     fwd_pass<0>(x, tw0);
@@ -609,6 +633,47 @@ struct KeyTex {
   }
 };
 
+// ---- shared prologue / epilogue pieces of every blind-rotate kernel ------------------------------------------------
+// test vector of gate g: CloudKey.BlindRotateTestvec, one LUT for all, a LUT per ciphertext, or an index into a LUT table
+template <int N>
+__device__ __forceinline__ const uint32_t* br_testvec(const BrArgs& A, long long g) {
+  if (!A.luts) return A.testvec;
+  const long long k = A.lut_index ? (long long)A.lut_index[g] : (A.nluts == 1 ? 0 : g);
+  return A.luts + k * (2 * N);
+}
+// mod switch (evaluator.go:116,122): a~ = ((a + 2^(30-NBIT)) mod 2^32) >> (31-NBIT).  lk > 0 (many-LUT bootstraps, no
+// reference counterpart): the switch goes to 2N / 2^lk levels, scaled back up, so that a~ is a multiple of 2^lk.
+template <int LOGN>
+__device__ __forceinline__ int br_modswitch(uint32_t a, int lk) {
+  return (int)(((a + (1u << (30 - LOGN + lk))) >> (31 - LOGN + lk)) << lk);
+}
+// b~ = 2N - ((int64(b) + 2^(30-NBIT)) >> (31-NBIT))  (the sum is taken in 64 bits: b~ = 0 when it carries)
+template <int LOGN>
+__device__ __forceinline__ int br_btilde(uint32_t b, int lk) {
+  const unsigned long long bb = (unsigned long long)b + (1ull << (30 - LOGN + lk));
+  return (int)((2 * (1 << LOGN) - (int)((bb >> (31 - LOGN + lk)) << lk)) & (2 * (1 << LOGN) - 1));
+}
+// epilogue: TRLWE (mode 0), sample extract at 0 (mode 1; trlwe/trlwe_ops.go:10-21: out[0] = A[0], out[i] = ~A[N-i],
+// out[N] = B[0]) or at indices 0..K-1 (mode 2; trlwe.SampleExtractIndex trlwe/trlwe.go:114-128: out[i] = A[k-i] for
+// i <= k, ~A[N+k-i] above, out[N] = B[k]).  PA / PB: the accumulator polynomials; tid / nt: this thread among the gate's.
+template <int N>
+__device__ __forceinline__ void br_write_output(const BrArgs& A, long long g, const uint32_t* PA, const uint32_t* PB, int tid, int nt) {
+  if (A.out_mode == 0) {
+    uint32_t* o = A.out + g * (2 * N);
+    for (int j = tid; j < N; j += nt) { o[j] = PA[j]; o[N + j] = PB[j]; }
+  } else if (A.out_mode == 1) {
+    uint32_t* o = A.out + g * (N + 1);
+    for (int j = tid; j < N; j += nt) o[j] = (j == 0) ? PA[0] : ~PA[N - j];
+    if (tid == 0) o[N] = PB[0];
+  } else {
+    for (int k = 0; k < A.extract_k; k++) {
+      uint32_t* o = A.out + (g * A.extract_k + k) * (N + 1);
+      for (int j = tid; j < N; j += nt) o[j] = (j <= k) ? PA[k - j] : ~PA[N + k - j];
+      if (tid == 0) o[N] = PB[k];
+    }
+  }
+}
+
 // Accumulator TRLWE in shared memory: [2 polynomials][EXT * N] words.  EXT = 1: the N coefficients.  EXT = 2: followed
 // by their complements, so that (X^k P)[j] (buffer_methods.go:133-164: P[idx] or ~P[idx - N], idx = (j - k) mod 2N) is
 // one load at idx.  EXT = 3: followed by the coefficients again, so that idx + offsets < 3N needs no wrap either.
@@ -625,6 +690,13 @@ struct AccBuf {
   }
 };
 
+// TFHE_BR_KEY_EARLY: the 16 key values of a multiply-accumulate are requested (pinned by volatile asm) 1 = right after the
+// barrier of the transform's first exchange, 2 = right after the barrier of its last exchange, instead of wherever ptxas
+// places the loads (mostly inside the last register pass, ~150 cycles before their use: ncu shows 5 % of all stall samples
+// on the first two DFMAs of the multiply-accumulate, waiting on L2).  Costs 64 registers for the time in between.
+#ifndef TFHE_BR_KEY_EARLY
+#define TFHE_BR_KEY_EARLY 0
+#endif
 template <int LOGN, int L, int BGBIT, bool SMALL, class Key>
 __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, false>& fft, const Key bk, int at,
                                                  uint32_t offset, const Tw4& tw0) {
@@ -701,6 +773,34 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
         x[a].x = digit_scaled<BGBIT>(dre[a], sh);
         x[a].y = digit_scaled<BGBIT>(dim[a], sh);
       }
+#if TFHE_BR_KEY_EARLY
+      if constexpr (std::is_same<Key, KeyLdg>::value) {
+        double2 kA[8], kB[8];
+        const int r = poly * L + lvl;
+        auto load_keys = [&]() {
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(kA[e].x), "=d"(kA[e].y) : "l"(bk.p + key_pos<T>(r, 0, e, tau)));
+            asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(kB[e].x), "=d"(kB[e].y) : "l"(bk.p + key_pos<T>(r, 1, e, tau)));
+          }
+        };
+        typename Fft<LOGN - 1, false>::NoHook nh;
+        if (TFHE_BR_KEY_EARLY == 1) fft.forward_hooks(x, tw0, load_keys, nh);
+        else fft.forward_hooks(x, tw0, nh, load_keys);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          accA[e].x = fma(x[e].x, kA[e].x, accA[e].x);
+          accA[e].x = fma(-x[e].y, kA[e].y, accA[e].x);
+          accA[e].y = fma(x[e].x, kA[e].y, accA[e].y);
+          accA[e].y = fma(x[e].y, kA[e].x, accA[e].y);
+          accB[e].x = fma(x[e].x, kB[e].x, accB[e].x);
+          accB[e].x = fma(-x[e].y, kB[e].y, accB[e].x);
+          accB[e].y = fma(x[e].x, kB[e].y, accB[e].y);
+          accB[e].y = fma(x[e].y, kB[e].x, accB[e].y);
+        }
+        continue;
+      }
+#endif
       fft.forward(x, tw0);
       mac(x, poly * L + lvl);
     }
@@ -727,6 +827,14 @@ constexpr size_t br_smem_bytes(int n) {
   return (size_t)8 * TFHE_BR_ACC_EXT * (1 << LOGN) /*acc*/ + (size_t)br_nbuf(LOGN) * TFHE_BR_EXW * (1 << (LOGN - 1)) * 16 /*exchange [NBUF][EXW][M]*/ +
          (size_t)(((n + 1) * 2 + 15) / 16 * 16) /*abar*/;
 }
+
+// Bulk L2 prefetch (TMA unit, no registers, no LSU wavefronts): cp.async.bulk.prefetch.L2 of `bytes` (multiple of 16) at p.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+#ifndef TFHE_BR_L2_PREFETCH
+#define TFHE_BR_L2_PREFETCH 1   // work items request the key rows of the NEXT chunk (and, at kernel start, of the first) into L2
+#endif
 
 // acquire / release on the per-gate progress words of the work-item hand-over
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -775,6 +883,21 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
 #ifdef TFHE_BR_STAGGER  // experiment: start the co-resident blocks of an SM a fraction of a step apart
   __nanosleep((blockIdx.x / 148u) * TFHE_BR_STAGGER);
 #endif
+#if TFHE_BR_L2_PREFETCH
+  // The key rows of a chunk are first touched by whichever blocks reach it first, and those wait out an HBM round trip
+  // per digit; at kernel start (cold L2) that is EVERY block.  A chunk's rows are therefore requested into L2 ahead of
+  // time, in slices, by the bulk-copy unit: chunk 0 by all blocks at entry, chunk c + 1 by the first items of chunk c.
+  constexpr int PF_SLICES = 256;
+  auto prefetch_chunk = [&](int ch, unsigned slice) {
+    const size_t lo = (size_t)ch * A.chunk_steps, hi = (size_t)min(n, (ch + 1) * A.chunk_steps);
+    if (lo >= hi) return;
+    const size_t bytes = (hi - lo) * row_stride * sizeof(double2), per = (bytes / PF_SLICES + 15) / 16 * 16;
+    const size_t off = (size_t)slice * per;
+    if (off < bytes)
+      prefetch_l2_bulk(reinterpret_cast<const char*>(A.bsk + lo * row_stride) + off, (uint32_t)min(per, bytes - off));
+  };
+  if (tau == 0 && blockIdx.x < PF_SLICES) prefetch_chunk(0, blockIdx.x);
+#endif
 
   for (;;) {
     if (tau == 0) s_item = atomicAdd(&A.ctl[0], 1u);
@@ -784,13 +907,15 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
     const int chunk = (int)(item / (unsigned long long)A.count);
     const long long g = (long long)(item - (unsigned long long)chunk * (unsigned long long)A.count);
     const int i0 = chunk * A.chunk_steps, i1 = min(n, i0 + A.chunk_steps);
+#if TFHE_BR_L2_PREFETCH
+    if (tau == 0 && g < PF_SLICES && chunk + 1 < A.nchunks) prefetch_chunk(chunk + 1, (unsigned)g);
+#endif
     const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
     // mod switch (evaluator.go:116,122): a~_i = ((a_i + 2^(30-NBIT)) mod 2^32) >> (31-NBIT)
-    for (int i = i0 + tau; i < i1; i += T) abar[i - i0] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
-    if (chunk == 0) {  // acc = X^btil * testvec, b~ = 2N - ((int64(b) + 2^(30-NBIT)) >> (31-NBIT))
-      const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
-      const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
-      const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+    for (int i = i0 + tau; i < i1; i += T) abar[i - i0] = (unsigned short)br_modswitch<LOGN>(ct[i], A.ms_log2k);
+    if (chunk == 0) {  // acc = X^btil * testvec
+      const int btil = br_btilde<LOGN>(ct[n], A.ms_log2k);
+      const uint32_t* __restrict__ tv = br_testvec<N>(A, g);
       for (int j = tau; j < N; j += T) {
         const int idx = (j - btil) & (2 * N - 1);
         const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
@@ -829,13 +954,8 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
       __threadfence();
       __syncthreads();
       if (tau == 0) st_release_gpu(A.progress + g, chunk + 1);
-    } else if (A.out_mode == 0) {
-      uint32_t* o = A.out + g * (2 * N);
-      for (int j = tau; j < N; j += T) { o[j] = acc[j]; o[N + j] = acc[AB::STRIDE + j]; }
-    } else {  // sample extract at 0 (trlwe_ops.go:10-21): out[0] = A[0], out[i] = ~A[N-i], out[N] = B[0]
-      uint32_t* o = A.out + g * (N + 1);
-      for (int j = tau; j < N; j += T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
-      if (tau == 0) o[N] = acc[AB::STRIDE];
+    } else {
+      br_write_output<N>(A, g, acc, acc + AB::STRIDE, tau, T);
     }
     __syncthreads();  // acc / abar / s_item are rewritten by the next item
   }

@@ -56,10 +56,9 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  for (int i = threadIdx.x; i < n; i += 2 * T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
-  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
-  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
-  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+  for (int i = threadIdx.x; i < n; i += 2 * T) abar[i] = (unsigned short)br_modswitch<LOGN>(ct[i], A.ms_log2k);
+  const int btil = br_btilde<LOGN>(ct[n], A.ms_log2k);
+  const uint32_t* __restrict__ tv = br_testvec<N>(A, g);
   for (int j = threadIdx.x; j < N; j += 2 * T) {
     const int idx = (j - btil) & (2 * N - 1);
     const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
@@ -151,14 +150,7 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_lat_ker
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 
-  if (A.out_mode == 0) {
-    uint32_t* o = A.out + g * (2 * N);
-    for (int j = threadIdx.x; j < 2 * N; j += 2 * T) o[j] = acc[j];
-  } else {  // sample extract at 0 (trlwe_ops.go:10-21)
-    uint32_t* o = A.out + g * (N + 1);
-    for (int j = threadIdx.x; j < N; j += 2 * T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
-    if (threadIdx.x == 0) o[N] = acc[N];
-  }
+  br_write_output<N>(A, g, acc, acc + N, (int)threadIdx.x, 2 * T);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -194,10 +186,9 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_latp_ke
   const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
   double2* my_stage = stage + (size_t)grp * L * 16 * T + tau;
 
-  for (int i = threadIdx.x; i < n; i += 2 * T) abar[i] = (unsigned short)((ct[i] + (1u << (30 - LOGN))) >> (31 - LOGN));
-  const unsigned long long bb = (unsigned long long)ct[n] + (1ull << (30 - LOGN));
-  const int btil = (int)((2 * N - (int)(bb >> (31 - LOGN))) & (2 * N - 1));
-  const uint32_t* __restrict__ tv = A.luts ? A.luts + (A.nluts == 1 ? 0 : g) * (2 * N) : A.testvec;
+  for (int i = threadIdx.x; i < n; i += 2 * T) abar[i] = (unsigned short)br_modswitch<LOGN>(ct[i], A.ms_log2k);
+  const int btil = br_btilde<LOGN>(ct[n], A.ms_log2k);
+  const uint32_t* __restrict__ tv = br_testvec<N>(A, g);
   for (int j = threadIdx.x; j < N; j += 2 * T) {
     const int idx = (j - btil) & (2 * N - 1);
     const uint32_t va = tv[idx & (N - 1)], vb = tv[N + (idx & (N - 1))];
@@ -296,14 +287,7 @@ __global__ void __launch_bounds__(2 * (1 << (LOGN - 4)), 1) blind_rotate_latp_ke
     __syncthreads();  // both polynomials updated, `cross` and the stage free
   }
 
-  if (A.out_mode == 0) {
-    uint32_t* o = A.out + g * (2 * N);
-    for (int j = threadIdx.x; j < 2 * N; j += 2 * T) o[j] = acc[j];
-  } else {
-    uint32_t* o = A.out + g * (N + 1);
-    for (int j = threadIdx.x; j < N; j += 2 * T) o[j] = (j == 0) ? acc[0] : ~acc[N - j];
-    if (threadIdx.x == 0) o[N] = acc[N];
-  }
+  br_write_output<N>(A, g, acc, acc + N, (int)threadIdx.x, 2 * T);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

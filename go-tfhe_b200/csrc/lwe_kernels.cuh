@@ -77,6 +77,14 @@ __global__ void mux_or_prepare_kernel(const uint32_t* __restrict__ x, const uint
     out[row + i] = x[row + i] + y[row + i] + (i == n ? 0x20000000u : 0u);
 }
 
+// Two-bootstrap MUX (opt-in, tfhe_ctx_set_mux_mode): the two AND results stay under the ring key (sample-extracted,
+// no key switch: gates.bootstrapWithoutKeySwitch gates/gates.go:145-149), their sum plus 1/8 is key-switched once.
+__global__ void mux_sum_kernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ y, uint32_t* __restrict__ out, int N) {
+  const long long g = blockIdx.x;
+  const size_t row = (size_t)g * (N + 1);
+  for (int i = threadIdx.x; i <= N; i += blockDim.x) out[row + i] = x[row + i] + y[row + i] + (i == N ? 0x20000000u : 0u);
+}
+
 // gather / scatter of ciphertext rows by index list (used to compact MUX jobs)
 __global__ void gather_rows_kernel(const uint32_t* __restrict__ src, const int* __restrict__ idx,
                                    uint32_t* __restrict__ dst, int words) {

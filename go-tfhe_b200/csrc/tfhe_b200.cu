@@ -93,6 +93,10 @@ struct tfhe_ctx {
   long long ks_K = 0;              // N * t * (base - 1); 0 = path unavailable for this parameter set
   CUtensorMap ks_mapB{};
   int ks_variant = 0;              // 0 = auto, 1 = row gather (key_switch_kernel), 2 = tensor-core contraction
+  int mux_mode = 0;                // 0 = the reference's three bootstraps per MUX, 1 = two blind rotations + one key switch
+  // proxy re-encryption key (proxyreenc.ProxyReencryptionKey.KeyEncryptions): [n*t*base][stride] rows under the target key
+  uint32_t* d_reenc = nullptr;
+  int reenc_stride = 0, reenc_basebit = 0, reenc_t = 0;
   DevBuf ks_sel;                   // selection matrix of the current chunk
   Tw4 tw0{};
   cudaStream_t stream = nullptr;  // used by the host-buffer API (compute)
@@ -349,13 +353,21 @@ void pick_chunks(const tfhe_ctx* c, int64_t count, int* nchunks, int* chunk_step
   }
 }
 
+// options of a blind rotation beyond the reference's: LUT table + index, many-LUT mod switch, multi-index extraction
+struct BrOpts {
+  const int* d_lut_index = nullptr;  // [count] indices into d_luts
+  int ms_log2k = 0;                  // mod switch keeps multiples of 2^ms_log2k
+  int extract_k = 0;                 // out_mode 2: samples at indices 0..extract_k-1
+};
+
 int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const uint32_t* d_luts, int64_t nluts,
-                        uint32_t* d_out, int out_mode, cudaStream_t s) {
+                        uint32_t* d_out, int out_mode, cudaStream_t s, const BrOpts& opt = BrOpts()) {
   if (count == 0) return 0;
   const Variant& V = kVariants[c->variant];
   BrArgs a{};
   a.ct_in = d_ct; a.testvec = c->d_testvec; a.luts = d_luts; a.nluts = nluts; a.bsk = c->d_bsk; a.tw_tab = c->d_tw;
   a.out = d_out; a.n = c->P.n; a.offset = c->offset; a.out_mode = out_mode; a.tw0 = c->tw0;
+  a.lut_index = opt.d_lut_index; a.ms_log2k = opt.ms_log2k; a.extract_k = opt.extract_k;
   a.count = count; a.nchunks = 1; a.chunk_steps = c->P.n;
   const int T = c->P.N / 16;
 #if TFHE_EXPERIMENTAL
@@ -409,8 +421,9 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
     BrArgs b = a;
     b.count = cnt;
     b.ct_in = d_ct + (size_t)g0 * (c->P.n + 1);
-    if (d_luts && nluts != 1) b.luts = d_luts + (size_t)g0 * 2 * c->P.N;
-    b.out = d_out + (size_t)g0 * (out_mode == 0 ? 2 * c->P.N : c->P.N + 1);
+    if (d_luts && nluts != 1 && !opt.d_lut_index) b.luts = d_luts + (size_t)g0 * 2 * c->P.N;
+    if (opt.d_lut_index) b.lut_index = opt.d_lut_index + g0;
+    b.out = d_out + (size_t)g0 * (out_mode == 0 ? 2 * c->P.N : (out_mode == 2 ? opt.extract_k : 1) * (c->P.N + 1));
     pick_chunks(c, cnt, &b.nchunks, &b.chunk_steps);
     const size_t ctl_bytes = 16 + (size_t)std::min<int64_t>(SUB, std::max<int64_t>(cnt, 1)) * sizeof(int);
     if (ctl_bytes > c->br_ctl.cap) {  // (re)allocated control words start at zero; the kernel leaves them at zero
@@ -536,6 +549,18 @@ int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32
 
 bool is_group(const tfhe_ctx* c) { return !c->kids.empty(); }
 
+// a setting applied to a group goes to every device
+#define GROUP_FORWARD(c, call)                                                   \
+  if ((c) && is_group(c)) {                                                      \
+    for (tfhe_ctx* k__ : (c)->kids) {                                            \
+      tfhe_ctx* kid = k__;                                                       \
+      const int rc__ = (call);                                                   \
+      if (rc__) { (c)->err = kid->err; return rc__; }                            \
+    }                                                                            \
+    return TFHE_OK;                                                              \
+  }
+
+
 // --- multi-device groups ------------------------------------------------------------------------------------------
 // Contiguous shards of [0, count) over the kids of a group, cut where the running COST (bootstraps) is closest to an even
 // split; cost == nullptr: equal counts.
@@ -581,18 +606,20 @@ int check_ready(tfhe_ctx* c, bool need_ksk) {
 }
 
 int bootstrap_device(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const uint32_t* d_luts, int64_t nluts,
-                     uint32_t* d_out, cudaStream_t s, const GateDesc* out_gates = nullptr, long long instances = 1) {
-  CK(c, c->lwe1.reserve((size_t)count * (c->P.N + 1) * 4));
+                     uint32_t* d_out, cudaStream_t s, const GateDesc* out_gates = nullptr, long long instances = 1,
+                     const BrOpts& opt = BrOpts()) {
+  const int64_t per = opt.extract_k > 0 ? opt.extract_k : 1;  // extracted samples (= key switches) per ciphertext
+  CK(c, c->lwe1.reserve((size_t)count * per * (c->P.N + 1) * 4));
   tfhe_ctx::StageEv ev{};
   if (c->timing && count > 0) {
     if (!c->ev_free.empty()) { ev = c->ev_free.back(); c->ev_free.pop_back(); }
     else { CK(c, cudaEventCreate(&ev.e0)); CK(c, cudaEventCreate(&ev.e1)); CK(c, cudaEventCreate(&ev.e2)); }
     CK(c, cudaEventRecord(ev.e0, s));
   }
-  int rc = launch_blind_rotate(c, count, d_ct, d_luts, nluts, c->lwe1.as<uint32_t>(), 1, s);
+  int rc = launch_blind_rotate(c, count, d_ct, d_luts, nluts, c->lwe1.as<uint32_t>(), opt.extract_k > 0 ? 2 : 1, s, opt);
   if (rc) return rc;
   if (c->timing && count > 0) CK(c, cudaEventRecord(ev.e1, s));
-  rc = launch_key_switch(c, count, c->lwe1.as<uint32_t>(), d_out, s, out_gates, instances);
+  rc = launch_key_switch(c, count * per, c->lwe1.as<uint32_t>(), d_out, s, out_gates, instances);
   if (rc) return rc;
   if (c->timing && count > 0) { CK(c, cudaEventRecord(ev.e2, s)); c->ev_live.push_back(ev); }
   return 0;
@@ -807,6 +834,7 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
 #endif
   if (c->d_ksk) cudaFree(c->d_ksk);
   if (c->d_ksk_bytes) cudaFree(c->d_ksk_bytes);
+  if (c->d_reenc) cudaFree(c->d_reenc);
   c->ks_sel.release();
   if (c->d_testvec) cudaFree(c->d_testvec);
   if (c->d_tw) cudaFree(c->d_tw);
@@ -1120,6 +1148,26 @@ int gate_batch_device_impl(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64
   c->launches++;
   CK(c, cudaGetLastError());
   int rc;
+  if (c->mux_mode == 1 && nm) {  // opt-in: MUX = KeySwitch(BR(AND(a,b)) + BR(ANDNY(a,c)) + 1/8) — two blind rotations, one key switch
+    const int N1 = c->P.N + 1;
+    CK(c, c->lwe1.reserve((size_t)j1 * N1 * 4));
+    CK(c, c->prep2.reserve((size_t)nm * N1 * 4));
+    uint32_t* ext = c->lwe1.as<uint32_t>();
+    if ((rc = launch_blind_rotate(c, j1, in1, nullptr, 0, ext, 1, s))) return rc;
+    if (nb) {
+      if ((rc = launch_key_switch(c, nb, ext, out1, s))) return rc;
+      scatter_rows_kernel<<<(unsigned)nb, 128, 0, s>>>(out1, d_src1, d_out, n1);
+      c->launches++;
+    }
+    mux_sum_kernel<<<(unsigned)nm, 256, 0, s>>>(ext + (size_t)nb * N1, ext + (size_t)(nb + nm) * N1, c->prep2.as<uint32_t>(), c->P.N);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    if ((rc = launch_key_switch(c, nm, c->prep2.as<uint32_t>(), out1, s))) return rc;
+    scatter_rows_kernel<<<(unsigned)nm, 128, 0, s>>>(out1, d_muxg, d_out, n1);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return TFHE_OK;
+  }
   if (j1 && (rc = bootstrap_device(c, j1, in1, nullptr, 0, out1, s))) return rc;
   if (nb) {
     scatter_rows_kernel<<<(unsigned)nb, 128, 0, s>>>(out1, d_src1, d_out, n1);
@@ -1217,31 +1265,64 @@ static int h2d(tfhe_ctx* c, DevBuf& b, const void* src, size_t bytes) {
   return 0;
 }
 
-int tfhe_bootstrap_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* luts, int64_t nluts,
-                         uint32_t* ct_out) {
+// Bootstraps with host buffers: the reference's form (luts == NULL / one LUT / a LUT per ciphertext), a LUT table with an
+// index per ciphertext (lut_index != NULL), and many-LUT bootstraps (log2k > 0: 2^log2k outputs per ciphertext).
+static int bootstrap_host(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* luts, int64_t nluts,
+                          const int32_t* lut_index, int log2k, uint32_t* ct_out) {
   int rc = check_ready(c, true);
   if (rc) return rc;
   if (count < 0 || (count > 0 && (!ct_in || !ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
-  if (luts && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
+  if (lut_index && (!luts || nluts < 1)) return fail(c, TFHE_ERR_ARG, "lut_index needs a LUT table");
+  if (luts && !lut_index && nluts != 1 && nluts != count) return fail(c, TFHE_ERR_ARG, "nluts must be 1 or count");
+  if (log2k < 0 || (1 << log2k) > c->P.N / 2) return fail(c, TFHE_ERR_ARG, "log2_k out of range");
+  if (log2k > 0 && !luts) return fail(c, TFHE_ERR_ARG, "a many-LUT bootstrap needs a packed LUT");
   if (count == 0) return TFHE_OK;
-  const size_t row = (size_t)(c->P.n + 1) * 4, lrow = (size_t)2 * c->P.N * 4;
+  if (lut_index)
+    for (int64_t g = 0; g < count; g++)
+      if (lut_index[g] < 0 || lut_index[g] >= nluts) return fail(c, TFHE_ERR_ARG, "lut_index[%lld] = %d out of range", (long long)g, (int)lut_index[g]);
+  const int64_t per = log2k > 0 ? (1ll << log2k) : 1;
+  const size_t n1 = (size_t)c->P.n + 1, row = n1 * 4, lrow = (size_t)2 * c->P.N * 4;
+  const bool per_ct = luts && !lut_index && nluts != 1;
   if (is_group(c)) {
-    const std::vector<int64_t> b = shard_bounds((int)c->kids.size(), count, nullptr, 0);
+    const std::vector<int64_t> bd = shard_bounds((int)c->kids.size(), count, nullptr, 0);
     return for_each_kid(c, [&](int d) {
-      const int64_t g0 = b[d], cnt = b[d + 1] - b[d];
-      return tfhe_bootstrap_batch(c->kids[d], cnt, ct_in + (size_t)g0 * (c->P.n + 1),
-                                  luts ? luts + (nluts == 1 ? 0 : (size_t)g0 * 2 * c->P.N) : nullptr, luts ? (nluts == 1 ? 1 : cnt) : 0,
-                                  ct_out + (size_t)g0 * (c->P.n + 1));
+      const int64_t g0 = bd[d], cnt = bd[d + 1] - bd[d];
+      return bootstrap_host(c->kids[d], cnt, ct_in + (size_t)g0 * n1, luts ? luts + (per_ct ? (size_t)g0 * 2 * c->P.N : 0) : nullptr,
+                            luts ? (per_ct ? cnt : nluts) : 0, lut_index ? lut_index + g0 : nullptr, log2k,
+                            ct_out + (size_t)g0 * per * n1);
     });
   }
   if ((rc = set_device(c))) return rc;
-  const bool per_ct = luts && nluts != 1;
-  if (luts && !per_ct && (rc = h2d(c, c->h2d_luts, luts, lrow))) return rc;
-  const HostIn in[2] = {{ct_in, row, &Slot::a}, {per_ct ? luts : nullptr, lrow, &Slot::luts}};
-  return run_pipelined(c, count, in, 2, ct_out, row, [&](Slot& sl, int64_t, int64_t cnt) {
+  if (luts && !per_ct && (rc = h2d(c, c->h2d_luts, luts, (size_t)nluts * lrow))) return rc;
+  const HostIn in[3] = {{ct_in, row, &Slot::a}, {per_ct ? luts : nullptr, lrow, &Slot::luts}, {lut_index, 4, &Slot::c}};
+  return run_pipelined(c, count, in, 3, ct_out, (size_t)per * row, [&](Slot& sl, int64_t, int64_t cnt) {
+    BrOpts opt;
+    opt.d_lut_index = lut_index ? sl.c.as<int>() : nullptr;
+    opt.ms_log2k = log2k;
+    opt.extract_k = log2k > 0 ? (int)per : 0;
     return bootstrap_device(c, cnt, sl.a.as<uint32_t>(), luts ? (per_ct ? sl.luts.as<uint32_t>() : c->h2d_luts.as<uint32_t>()) : nullptr,
-                            luts ? (per_ct ? cnt : 1) : 0, sl.out.as<uint32_t>(), c->stream);
+                            luts ? (per_ct ? cnt : nluts) : 0, sl.out.as<uint32_t>(), c->stream, nullptr, 1, opt);
   });
+}
+
+int tfhe_bootstrap_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* luts, int64_t nluts,
+                         uint32_t* ct_out) {
+  if (!c) return TFHE_ERR_ARG;
+  return bootstrap_host(c, count, ct_in, luts, nluts, nullptr, 0, ct_out);
+}
+
+int tfhe_bootstrap_batch_indexed(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* luts, int64_t nluts,
+                                 const int32_t* lut_index, uint32_t* ct_out) {
+  if (!c) return TFHE_ERR_ARG;
+  if (!lut_index) return fail(c, TFHE_ERR_ARG, "lut_index is NULL");
+  return bootstrap_host(c, count, ct_in, luts, nluts, lut_index, 0, ct_out);
+}
+
+int tfhe_bootstrap_multi_lut_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, const uint32_t* packed_luts,
+                                   int64_t nluts, int32_t log2_k, uint32_t* ct_out) {
+  if (!c) return TFHE_ERR_ARG;
+  if (log2_k < 1) return fail(c, TFHE_ERR_ARG, "log2_k must be >= 1 (use tfhe_bootstrap_batch for one function)");
+  return bootstrap_host(c, count, ct_in, packed_luts, nluts, nullptr, log2_k, ct_out);
 }
 
 int tfhe_gate_batch(tfhe_ctx* c, int64_t count, const uint8_t* ops, int64_t nops, const uint32_t* a, const uint32_t* b,
@@ -1361,6 +1442,66 @@ int tfhe_key_switch_batch(tfhe_ctx* c, int64_t count, const uint32_t* lwe_in, ui
 
 
 static int h2d(tfhe_ctx* c, DevBuf& b, const void* src, size_t bytes);
+
+// ---- proxy re-encryption on the key-switch kernel (proxyreenc/proxyreenc.go:321-366) ------------------------------------
+// ReencryptTLWELv0 is IdentityKeySwitching with source dimension n instead of N: out = (0,..,0,b) - sum over the non-zero
+// digits k of a_i + 2^(31 - basebit t) of KeyEncryptions[base t i + base j + k].  The key is uploaded once per context.
+int tfhe_ctx_load_reencryption_key(tfhe_ctx* c, const uint32_t* key_encryptions, int32_t basebit, int32_t t) {
+  GROUP_FORWARD(c, tfhe_ctx_load_reencryption_key(kid, key_encryptions, basebit, t));
+  if (!c || !key_encryptions) return fail(c, TFHE_ERR_ARG, "null argument");
+  if (basebit < 1 || t < 1 || basebit * t > 31) return fail(c, TFHE_ERR_ARG, "invalid re-encryption decomposition");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int n = c->P.n;
+  if ((size_t)n * t * 4 > 128 * 1024) return fail(c, TFHE_ERR_ARG, "n * t too large for the key-switch kernel");
+  const size_t rows = (size_t)n * t * (1u << basebit);
+  const int stride = (n + 1 + 3) / 4 * 4;
+  DevBuf st;
+  CK(c, st.reserve(rows * (n + 1) * 4));
+  if (c->d_reenc) { cudaFree(c->d_reenc); c->d_reenc = nullptr; }
+  CK(c, cudaMalloc(&c->d_reenc, rows * stride * 4));
+  CK(c, cudaMemcpyAsync(st.p, key_encryptions, rows * (n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+  ksk_repack_kernel<<<(unsigned)rows, 128, 0, c->stream>>>(st.as<uint32_t>(), c->d_reenc, n + 1, stride, 1 << basebit);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  CK(c, cudaStreamSynchronize(c->stream));
+  st.release();
+  c->reenc_stride = stride; c->reenc_basebit = basebit; c->reenc_t = t;
+  return TFHE_OK;
+}
+
+int tfhe_reencrypt_batch(tfhe_ctx* c, int64_t count, const uint32_t* ct_in, uint32_t* ct_out) {
+  if (!c) return TFHE_ERR_ARG;
+  if (count < 0 || (count > 0 && (!ct_in || !ct_out))) return fail(c, TFHE_ERR_ARG, "bad batch arguments");
+  if (count == 0) return TFHE_OK;
+  const size_t n1 = (size_t)c->P.n + 1;
+  if (is_group(c)) {
+    const std::vector<int64_t> bd = shard_bounds((int)c->kids.size(), count, nullptr, 0);
+    return for_each_kid(c, [&](int d) {
+      return tfhe_reencrypt_batch(c->kids[d], bd[d + 1] - bd[d], ct_in + (size_t)bd[d] * n1, ct_out + (size_t)bd[d] * n1);
+    });
+  }
+  if (!c->d_reenc) return fail(c, TFHE_ERR_STATE, "re-encryption key not loaded");
+  int rc = set_device(c);
+  if (rc) return rc;
+  const int n = c->P.n;
+  const size_t sm = (size_t)n * c->reenc_t * sizeof(uint32_t);
+  const int threads = std::min(512, std::max(128, (c->reenc_stride / 4 + 31) / 32 * 32));
+  const HostIn in[1] = {{ct_in, n1 * 4, &Slot::a}};
+  return run_pipelined(c, count, in, 1, ct_out, n1 * 4, [&](Slot& sl, int64_t, int64_t cnt) {
+    const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(64, (2 * (int64_t)c->sm_count) / cnt));
+    if (splits > 1) {
+      zero_out_rows_kernel<<<(unsigned)cnt, 128, 0, c->stream>>>(sl.out.as<uint32_t>(), n, nullptr, 1);
+      c->launches++;
+    }
+    key_switch_kernel<<<dim3((unsigned)cnt, (unsigned)splits), threads, sm, c->stream>>>(
+        sl.a.as<uint32_t>(), c->d_reenc, sl.out.as<uint32_t>(), /*source dimension*/ n, /*target dimension*/ n, c->reenc_basebit,
+        c->reenc_t, c->reenc_stride, nullptr, 1, splits);
+    c->launches++;
+    CK(c, cudaGetLastError());
+    return 0;
+  });
+}
 
 // ---- levelised circuit runner --------------------------------------------------------------------------
 int tfhe_circuit_run(tfhe_ctx* c, int64_t instances, int32_t n_inputs, int32_t n_gates, const tfhe_gate_desc* gates,
@@ -1529,17 +1670,6 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) {
   return total;
 }
 
-// a setting applied to a group goes to every device
-#define GROUP_FORWARD(c, call)                                                   \
-  if ((c) && is_group(c)) {                                                      \
-    for (tfhe_ctx* k__ : (c)->kids) {                                            \
-      tfhe_ctx* kid = k__;                                                       \
-      const int rc__ = (call);                                                   \
-      if (rc__) { (c)->err = kid->err; return rc__; }                            \
-    }                                                                            \
-    return TFHE_OK;                                                              \
-  }
-
 int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
   GROUP_FORWARD(c, tfhe_ctx_set_key_switch_variant(kid, variant));
   if (!c || variant < 0 || variant > 2) return fail(c, TFHE_ERR_ARG, "key-switch variant must be 0 (auto), 1 (gather) or 2 (tensor core)");
@@ -1583,6 +1713,16 @@ int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* c, int variant) {
   return fail(c, TFHE_ERR_ARG, "blind-rotate variant %d is an experimental kernel: rebuild with -DTFHE_EXPERIMENTAL=1 "
                                "(default library: 0 = automatic, 9 = lat, 10 = throughput kernel only, 12 = latp)", variant);
 #endif
+}
+
+// MUX evaluation: 0 = gates.MUX of the reference (gates/gates.go:107-114: OR(AND(a,b), AND(NOT a, c)), three bootstraps,
+// bit-identical to it), 1 = the two ANDs are blind-rotated and extracted WITHOUT key switch (gates.go:145-149), summed
+// with 1/8 and key-switched once: one blind rotation fewer, same truth table, different (valid) ciphertext words.
+int tfhe_ctx_set_mux_mode(tfhe_ctx* c, int mode) {
+  GROUP_FORWARD(c, tfhe_ctx_set_mux_mode(kid, mode));
+  if (!c || mode < 0 || mode > 1) return fail(c, TFHE_ERR_ARG, "mux mode must be 0 (three bootstraps) or 1 (two blind rotations + one key switch)");
+  c->mux_mode = mode;
+  return TFHE_OK;
 }
 
 // CMUX steps per work item of the persistent throughput kernel: 0 = automatic, >= n = whole gates per item.

@@ -132,6 +132,45 @@ class Context:
         self._ck(self.lib.tfhe_bootstrap_batch(self.h, len(ct), _ptr(ct), _ptr(l), nl, _ptr(out)), "tfhe_bootstrap_batch")
         return out
 
+    def bootstrap_batch_indexed(self, ct_in, luts, lut_index):
+        """LUT table [nluts][2][N] + one index per ciphertext (tfhe_bootstrap_batch_indexed)."""
+        P = self.P
+        ct = _u32(ct_in, (-1, P.n + 1))
+        l = _u32(luts, (-1, 2 * P.N))
+        idx = np.ascontiguousarray(lut_index, dtype=np.int32).ravel()
+        assert len(idx) == len(ct)
+        out = np.empty_like(ct)
+        self._ck(self.lib.tfhe_bootstrap_batch_indexed(self.h, len(ct), _ptr(ct), _ptr(l), len(l), _ptr(idx), _ptr(out)),
+                 "tfhe_bootstrap_batch_indexed")
+        return out
+
+    def bootstrap_multi_lut_batch(self, ct_in, packed_luts, log2_k):
+        """2^log2_k functions per ciphertext from one blind rotation -> [count][k][n+1] (tfhe_bootstrap_multi_lut_batch)."""
+        P = self.P
+        ct = _u32(ct_in, (-1, P.n + 1))
+        l = _u32(packed_luts, (-1, 2 * P.N))
+        out = np.empty((len(ct), 1 << log2_k, P.n + 1), dtype=np.uint32)
+        self._ck(self.lib.tfhe_bootstrap_multi_lut_batch(self.h, len(ct), _ptr(ct), _ptr(l), len(l), int(log2_k), _ptr(out)),
+                 "tfhe_bootstrap_multi_lut_batch")
+        return out
+
+    def load_reencryption_key(self, key_encryptions, basebit, t):
+        """proxyreenc.ProxyReencryptionKey.KeyEncryptions flattened [n*t*base][n+1]."""
+        k = _u32(key_encryptions)
+        assert k.size == self.P.n * t * (1 << basebit) * (self.P.n + 1)
+        self._ck(self.lib.tfhe_ctx_load_reencryption_key(self.h, _ptr(k), int(basebit), int(t)), "tfhe_ctx_load_reencryption_key")
+
+    def reencrypt_batch(self, ct_in):
+        """proxyreenc.ReencryptTLWELv0 for a batch."""
+        ct = _u32(ct_in, (-1, self.P.n + 1))
+        out = np.empty_like(ct)
+        self._ck(self.lib.tfhe_reencrypt_batch(self.h, len(ct), _ptr(ct), _ptr(out)), "tfhe_reencrypt_batch")
+        return out
+
+    def set_mux_mode(self, mode):
+        """0 = the reference's three-bootstrap MUX (default), 1 = two blind rotations + one key switch (opt-in)."""
+        self._ck(self.lib.tfhe_ctx_set_mux_mode(self.h, int(mode)), "tfhe_ctx_set_mux_mode")
+
     def gate_batch(self, ops, a, b=None, c=None):
         P = self.P
         a = _u32(a, (-1, P.n + 1))

@@ -31,3 +31,14 @@ class Generator:
 
 def NewGenerator(messageModulus, P):
     return Generator(messageModulus, P)
+
+
+def PackLookUpTables(luts):
+    """Test vector of a many-LUT bootstrap (tfhe_bootstrap_multi_lut_batch): k = len(luts) (a power of two) LookUpTables of
+    the same message modulus interleaved coefficient-wise, packed[j] = luts[j mod k][j].  Returns a TRLWE [2][N]."""
+    k = len(luts)
+    assert k >= 2 and k & (k - 1) == 0, "the number of functions must be a power of two"
+    polys = np.stack([np.asarray(l.Poly if hasattr(l, "Poly") else l, dtype=np.uint32).reshape(2, -1) for l in luts])
+    N = polys.shape[2]
+    j = np.arange(N)
+    return np.ascontiguousarray(polys[j % k, :, j].T)

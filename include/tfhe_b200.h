@@ -120,6 +120,23 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* ctx, uint32_t decomposition_offset, 
 int tfhe_bootstrap_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* ct_in, const uint32_t* luts,
                          int64_t nluts, uint32_t* ct_out);
 
+/* The same with a LUT TABLE and one index per ciphertext: luts [nluts][2][N], lut_index [count] with values in
+ * [0, nluts) (host memory).  What BootstrapLUTAssign callers that reuse a handful of functions want
+ * (examples/add_two_numbers/main.go:59-72 builds three LUTs for every nibble): 16 KiB per LUT cross the bus instead of
+ * 16 KiB per ciphertext.  Results equal tfhe_bootstrap_batch with the LUTs expanded. */
+int tfhe_bootstrap_batch_indexed(tfhe_ctx* ctx, int64_t count, const uint32_t* ct_in, const uint32_t* luts,
+                                 int64_t nluts, const int32_t* lut_index, uint32_t* ct_out);
+
+/* Many-LUT programmable bootstrap (additive; no reference counterpart): 2^log2_k functions of every ciphertext from ONE
+ * blind rotation.  The mod switch goes to 2N / 2^log2_k levels (scaled back, so every rotation is a multiple of 2^log2_k),
+ * the test vector interleaves the functions (packed[j] = lut_{j mod k}[j], k = 2^log2_k, all built by
+ * lut.Generator.GenLookUpTable for the same message modulus), and after the rotation the samples at indices 0..k-1
+ * (trlwe.SampleExtractIndex, trlwe/trlwe.go:114-128) are key-switched: ct_out [count][k][n+1], output i decrypts to
+ * f_i(message).  Costs log2_k bits of the mod-switch precision (the usual many-LUT trade).  packed_luts: nluts in
+ * {1, count} test vectors [nluts][2][N]. */
+int tfhe_bootstrap_multi_lut_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* ct_in, const uint32_t* packed_luts,
+                                   int64_t nluts, int32_t log2_k, uint32_t* ct_out);
+
 /* count gates.  Replaces gates.{NAND..ORYN,MUX,NOT,Copy} (gates/gates.go:26-130) and
  * gates.Batch{NAND,AND,OR,XOR,NOR,XNOR} (gates/gates.go:156-312; every element equals the
  * single-gate path, and XNOR uses the single-gate bias, see SURVEY.md section 2 defects 1-2).
@@ -147,6 +164,14 @@ int tfhe_sample_extract_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* trlw
 /* Identity key switch N -> n (trgsw/keyswitch.go:10-37, trgsw/trgsw.go:285-311):
  * LWE [count][N+1] -> LWE [count][n+1]. */
 int tfhe_key_switch_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* lwe_in, uint32_t* ct_out);
+
+/* --- proxy re-encryption (proxyreenc/proxyreenc.go) on the key-switch kernel ------------------------------------------- */
+/* Uploads proxyreenc.ProxyReencryptionKey.KeyEncryptions flattened as [n*t*base][n+1] (row index base*t*i + base*j + k,
+ * proxyreenc.go:272-290; k = 0 rows are never read), with its Base = 2^basebit and T = t. */
+int tfhe_ctx_load_reencryption_key(tfhe_ctx* ctx, const uint32_t* key_encryptions, int32_t basebit, int32_t t);
+/* proxyreenc.ReencryptTLWELv0 (proxyreenc.go:321-366) for every ciphertext: [count][n+1] under the source key ->
+ * [count][n+1] under the target key.  Bit-identical to the reference (u32 arithmetic). */
+int tfhe_reencrypt_batch(tfhe_ctx* ctx, int64_t count, const uint32_t* ct_in, uint32_t* ct_out);
 
 /* --- polynomial transforms at API granularity (reference FourierPoly layout in and out) ---------------------- */
 /* poly.Evaluator.ToFourierPolyAssign (poly/fourier_transform.go:18-21): [count][N] u32 -> [count][N] f64, unscaled,
@@ -195,6 +220,11 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* ctx);
  * (bit-identical for every set).  All compute identical results.  Values 1-8, 11, 13 name the measured-slower round-1
  * experiments (profiles/r01_experiments.md) and exist only in a library built with -DTFHE_EXPERIMENTAL=1. */
 int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
+/* How TFHE_OP_MUX is evaluated.  0 (default) = exactly gates.MUX (gates/gates.go:107-114): OR(AND(a,b), AND(NOT a, c)),
+ * three bootstraps, bit-identical to the reference.  1 (opt-in) = the two ANDs are blind-rotated and sample-extracted
+ * without key switch (gates.bootstrapWithoutKeySwitch, gates.go:145-149), summed with 1/8 and key-switched once: two blind
+ * rotations instead of three; same truth table, but NOT the reference's ciphertext words (hence opt-in). */
+int tfhe_ctx_set_mux_mode(tfhe_ctx* ctx, int mode);
 /* The throughput kernel runs persistent blocks over WORK ITEMS of `steps` consecutive CMUX steps of one gate (the
  * accumulator is handed from item to item through device memory), so that a batch that is not a multiple of the
  * resident blocks still fills the SMs to the end.  0 = automatic (default: whole gates for batches that fit the

@@ -648,6 +648,28 @@ void oracle_sample_extract0(const uint32_t* trlwe, int N, uint32_t* out) { sampl
 void oracle_key_switch(const oracle_params* P, const uint32_t* src, const uint32_t* ksk, uint32_t* out) {
   key_switch(*P, src, ksk, out);
 }
+
+// proxyreenc.ReencryptTLWELv0 (proxyreenc/proxyreenc.go:321-366).  key: KeyEncryptions flattened [n*t*base][n+1] with row
+// idx = base*t*i + base*j + k (proxyreenc.go:286); base = 2^basebit and t are the key's own (ProxyReencryptionKey.Base, .T).
+void oracle_reencrypt(const oracle_params* P, const uint32_t* ct_from, const uint32_t* key, int basebit, int t, uint32_t* out) {
+  const int n = P->n, base = 1 << basebit;
+  for (int x = 0; x <= n; x++) out[x] = 0;
+  out[n] = ct_from[n];                                              // :338-339 result.SetB(ctFrom.B())
+  const Torus prec = (Torus)1 << (32 - (1 + basebit * t));          // :342
+  for (int i = 0; i < n; i++) {                                     // :345
+    const Torus abar = ct_from[i] + prec;                           // :347
+    for (int j = 0; j < t; j++) {                                   // :350
+      const int shift = 32 - (j + 1) * basebit;                     // :352
+      const Torus mask = ((Torus)1 << basebit) - 1;                 // :353
+      const Torus k = (abar >> shift) & mask;                       // :354
+      if (k != 0) {                                                 // :356
+        const size_t idx = (size_t)base * t * i + (size_t)base * j + (size_t)k;  // :358
+        const Torus* row = key + idx * (n + 1);
+        for (int x = 0; x <= n; x++) out[x] = out[x] - row[x];      // :361-363
+      }
+    }
+  }
+}
 int oracle_gate_prepare(const oracle_params* P, int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   return gate_prepare(*P, op, a, b, out);
 }

@@ -160,6 +160,25 @@ def key_switch(P, src, ksk):
     return out
 
 
+def reencrypt(P, ct_from, key, basebit, t):
+    """proxyreenc.ReencryptTLWELv0 (proxyreenc/proxyreenc.go:321-366); key = KeyEncryptions [n*t*base][n+1]."""
+    out = np.zeros(P.n + 1, dtype=np.uint32)
+    lib().oracle_reencrypt(ctypes.byref(P), _p(np.ascontiguousarray(ct_from, dtype=np.uint32)),
+                           _p(np.ascontiguousarray(key, dtype=np.uint32)), ctypes.c_int(basebit), ctypes.c_int(t), _p(out))
+    return out
+
+
+def sample_extract_index(trlwe, N, k):
+    """trlwe.SampleExtractIndex (trlwe/trlwe.go:114-128): out[i] = A[k-i] (i <= k), 0xFFFFFFFF - A[N+k-i] (i > k), out[N] = B[k]."""
+    t = np.ascontiguousarray(trlwe, dtype=np.uint32).ravel()
+    A, B = t[:N], t[N:]
+    out = np.zeros(N + 1, dtype=np.uint32)
+    i = np.arange(N)
+    out[:N] = np.where(i <= k, A[(k - i) % N], np.uint32(0xFFFFFFFF) - A[(N + k - i) % N])
+    out[N] = B[k]
+    return out
+
+
 def gate_prepare(P, op, a, b):
     out = np.zeros(P.n + 1, dtype=np.uint32)
     rc = lib().oracle_gate_prepare(ctypes.byref(P), ctypes.c_int(OPS[op] if isinstance(op, str) else op),

@@ -1,0 +1,285 @@
+"""Reference-pinned parity: golden vectors made by the UNMODIFIED Go reference (go/cmd/mkgolden) checked against the CPU
+oracle (no GPU needed) and against the CUDA engine (-m gpu).
+
+The files live under tests/golden/go/<set>/{secret,cloud,vectors}.tfhb.  They cannot be produced in the build image (no Go
+toolchain) and a cloud key is 110-170 MB per set, so they are generated where Go exists and dropped in; when they are
+absent the tests SKIP WITH A LOUD REASON and ciphertext-level parity to the Go reference stays "unpinned" (DESIGN.md
+section 2).  To keep the checker itself honest, test_golden_kit_self_check builds the same files from the oracle into a
+temporary directory, runs the very same comparison on them, and shows that a single flipped output word is caught.
+
+Bar (the same for oracle-vs-Go and GPU-vs-Go): bit-exact torus words on the 80/110/128-bit sets for every vector; on the
+Uint sets decoded messages exact and phases within the per-set tolerance of tests/test_gpu_parity.py::UINT_TOL."""
+import glob
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "go")
+EXACT = {"80", "110", "128"}
+GATE_TAGS = {"NAND": "NAND", "AND": "AND", "OR": "OR", "XOR": "XOR", "XNOR": "XNOR", "NOR": "NOR", "ANNY": "ANDNY",
+             "ANYN": "ANDYN", "ORNY": "ORNY", "ORYN": "ORYN"}
+# phase tolerance (torus LSB) after blind rotate / after key switch for the sets whose f64 sums are not exact; ~4x the
+# worst case observed GPU-vs-oracle in round 1 (tests/test_gpu_parity.py prints the observed values)
+UINT_TOL = {"uint1": (1 << 4, 1 << 22), "uint2": (1 << 23, 1 << 25), "uint3": (1 << 22, 1 << 24), "uint4": (1 << 22, 1 << 23),
+            "uint5": (1 << 22, 1 << 22)}
+
+
+def present_sets():
+    return sorted(os.path.basename(os.path.dirname(p)) for p in glob.glob(os.path.join(GOLD, "*", "vectors.tfhb")))
+
+
+class _View:
+    pass
+
+
+def load_set(T, O, directory, name):
+    """-> (oracle params, oracle-style secret key view, oracle-style cloud key view, {tag: array})."""
+    OP = O.get_params(name)
+    P = T.params.get(name)
+    sk = T.wire.loads_secret_key(open(os.path.join(directory, "secret.tfhb"), "rb").read(), P)
+    ck = T.wire.loads_cloud_key(open(os.path.join(directory, "cloud.tfhb"), "rb").read(), P)
+    _, vec = T.wire.loads_bundle(open(os.path.join(directory, "vectors.tfhb"), "rb").read(), P)
+    osk = O.SecretKey(OP, 1)
+    osk.s0, osk.s1 = sk.KeyLv0.copy(), sk.KeyLv1.copy()
+    ock = _View()
+    ock.P, ock.offset, ock.testvec = OP, ck.DecompositionOffset, np.ascontiguousarray(ck.BlindRotateTestvec.ravel())
+    ock.ksk, ock.bsk_fft = ck.KeySwitchingKey, ck.BootstrappingKey
+    return OP, osk, ock, ck, vec
+
+
+def _centered(d):
+    return (np.asarray(d, dtype=np.int64) + (1 << 31)) % (1 << 32) - (1 << 31)
+
+
+def _lwe1_phase(ext, s1):
+    dot = int(np.sum(ext[:-1].astype(np.uint64) * s1.astype(np.uint64)) % (1 << 32))
+    return (int(ext[-1]) - dot) % (1 << 32)
+
+
+class OracleImpl:
+    """The implementation under test = the CPU oracle."""
+
+    def __init__(self, O, OP, ock):
+        self.O, self.P, self.ck, self.ev = O, OP, ock, O.Evaluator(OP.N)
+
+    def to_fourier(self, p):
+        return self.ev.to_fourier(p)
+
+    def external_product(self, row, c1):
+        return np.stack([self.ev.external_product(self.P, self.ck.bsk_fft[row], c, self.ck.offset) for c in c1])
+
+    def cmux(self, row, c0, c1):
+        return np.stack([self.ev.cmux(self.P, self.ck.bsk_fft[row], a, b, self.ck.offset) for a, b in zip(c0, c1)])
+
+    def gate(self, op, a, b, c=None):
+        if op == "MUX":
+            return self.O.mux(self.ck, a, b, c)
+        if op == "NOT":
+            return self.O.NOT(a)
+        if op == "COPY":
+            return a.copy()
+        return self.O.gate_batch(self.ck, op, a, b)
+
+    def blind_rotate(self, ct, lut=None):
+        tv = self.ck.testvec if lut is None else lut
+        return np.stack([self.ev.blind_rotate(self.P, c, tv, self.ck.bsk_fft, self.ck.offset) for c in ct])
+
+    def bootstrap(self, ct, lut=None):
+        return self.O.bootstrap_batch(self.ck, ct, None if lut is None else np.asarray(lut).reshape(1, -1))
+
+
+class GpuImpl:
+    """The implementation under test = the CUDA engine through the C ABI."""
+
+    def __init__(self, T, name, ck):
+        self.P = T.params.get(name)
+        self.ctx = T.Context(self.P, 0)
+        self.ctx.load_cloudkey(ck.DecompositionOffset, ck.BootstrappingKey, ck.KeySwitchingKey, ck.BlindRotateTestvec)
+
+    def close(self):
+        self.ctx.close()
+
+    def to_fourier(self, p):
+        return self.ctx.to_fourier_batch(p.reshape(1, -1))[0]
+
+    def external_product(self, row, c1):
+        return self.ctx.cmux_batch(row, None, c1).reshape(len(c1), -1)
+
+    def cmux(self, row, c0, c1):
+        return self.ctx.cmux_batch(row, c0, c1).reshape(len(c1), -1)
+
+    def gate(self, op, a, b, c=None):
+        return self.ctx.gate_batch(op, a, b, c)
+
+    def blind_rotate(self, ct, lut=None):
+        return self.ctx.blind_rotate_batch(ct, lut).reshape(len(ct), -1)
+
+    def bootstrap(self, ct, lut=None):
+        return self.ctx.bootstrap_batch(ct, lut)
+
+
+def check_vectors(impl, name, OP, osk, vec, fourier_rtol):
+    """Every vector of a bundle against `impl`; returns the number of checks made."""
+    N, n = OP.N, OP.n
+    exact = name in EXACT
+    checks = 0
+    # polynomial transform: same evaluation points, order and packing; values within fourier_rtol of the reference's
+    fp = impl.to_fourier(vec["polp"].astype(np.uint32))
+    assert np.max(np.abs(fp - vec["polf"])) <= fourier_rtol * np.max(np.abs(vec["polf"])), "ToFourierPoly"
+    checks += 1
+    # external product / CMUX on the reference's own rows
+    c0, c1 = vec["ec0"].reshape(-1, 2 * N), vec["ec1"].reshape(-1, 2 * N)
+    eout, cout = vec["eout"].reshape(-1, 2 * N), vec["cout"].reshape(-1, 2 * N)
+    per = len(c1) // len(vec["erow"])
+    for k, row in enumerate(vec["erow"]):
+        sl = slice(k * per, (k + 1) * per)
+        got_e, got_c = impl.external_product(int(row), c1[sl]), impl.cmux(int(row), c0[sl], c1[sl])
+        if exact:
+            assert np.array_equal(got_e, eout[sl]) and np.array_equal(got_c, cout[sl]), "external product / CMUX row %d" % row
+        else:  # one external product of the L = 1 sets: off by ~2^7 LSB; stated tolerance 2^12
+            assert np.abs(_centered(got_e.astype(np.int64) - eout[sl].astype(np.int64))).max() <= (1 << 12)
+            assert np.abs(_centered(got_c.astype(np.int64) - cout[sl].astype(np.int64))).max() <= (1 << 12)
+        checks += 2
+    if "ina" in vec:  # Boolean set
+        a, b, c = (vec[t].reshape(-1, n + 1).astype(np.uint32) for t in ("ina", "inb", "inc"))
+        bits = vec["bits"]
+        A, B, C = bits & 1, (bits >> 1) & 1, (bits >> 2) & 1
+        truth = {"NAND": 1 - (A & B), "AND": A & B, "OR": A | B, "XOR": A ^ B, "XNOR": 1 - (A ^ B), "NOR": 1 - (A | B),
+                 "ANDNY": (1 - A) & B, "ANDYN": A & (1 - B), "ORNY": (1 - A) | B, "ORYN": A | (1 - B)}
+        for tag, op in GATE_TAGS.items():
+            want = vec[tag].reshape(-1, n + 1)
+            assert list(osk.decrypt_bool(want)) == list(truth[op]), "the Go output of %s does not decrypt to its truth table" % op
+            assert np.array_equal(impl.gate(op, a, b), want), op
+            checks += 1
+        assert np.array_equal(impl.gate("MUX", a, b, c), vec["MUX"].reshape(-1, n + 1)), "MUX"
+        assert list(osk.decrypt_bool(vec["MUX"].reshape(-1, n + 1))) == list(np.where(A == 1, B, C))
+        assert np.array_equal(impl.gate("NOT", a, None), vec["NOT"].reshape(-1, n + 1)), "NOT"
+        assert np.array_equal(impl.gate("COPY", a, None), vec["COPY"].reshape(-1, n + 1)), "COPY"
+        assert np.array_equal(impl.blind_rotate(a), vec["rot"].reshape(-1, 2 * N)), "BlindRotateAssign"
+        assert np.array_equal(impl.bootstrap(a), vec["boot"].reshape(-1, n + 1)), "BootstrapAssign"
+        checks += 5
+    else:  # message set: programmable bootstraps
+        m = int(vec["mmod"][0])
+        ct = vec["ct"].reshape(-1, n + 1).astype(np.uint32)
+        msgs = vec["msgs"].astype(np.int64)
+        luts = vec["luts"].reshape(3, 2 * N).astype(np.uint32)
+        fs = [lambda x: x, lambda x: (m - 1) - x, lambda x: x % (m // 2) if m > 2 else x]
+        tol_br, tol_ks = UINT_TOL.get(name, (0, 0))
+        for k in range(3):
+            want_rot, want = vec["rot%d" % k].reshape(-1, 2 * N), vec["pbs%d" % k].reshape(-1, n + 1)
+            assert list(osk.decrypt_message(want, m)) == [fs[k](int(x)) for x in msgs], "the Go PBS output does not decode"
+            got_rot, got = impl.blind_rotate(ct, luts[k]), impl.bootstrap(ct, luts[k])
+            assert list(osk.decrypt_message(got, m)) == [fs[k](int(x)) for x in msgs], "PBS %d decode" % k
+            if exact:
+                assert np.array_equal(got_rot, want_rot) and np.array_equal(got, want)
+            else:
+                O = importlib.import_module("oracle.oracle")
+                ph_g = np.array([_lwe1_phase(O.sample_extract0(r, N), osk.s1) for r in got_rot])
+                ph_w = np.array([_lwe1_phase(O.sample_extract0(r, N), osk.s1) for r in want_rot])
+                assert np.abs(_centered(ph_g - ph_w)).max() <= tol_br, "phase after blind rotate, LUT %d" % k
+                d = _centered(osk.phase(got).astype(np.int64) - osk.phase(want).astype(np.int64))
+                assert np.abs(d).max() <= tol_ks, "phase after key switch, LUT %d" % k
+            checks += 2
+    return checks
+
+
+def write_set_with_oracle(T, O, directory, name, count=8):
+    """The files go/cmd/mkgolden writes, made by the ORACLE instead of Go (self-check of the kit only)."""
+    OP, P = O.get_params(name), T.params.get(name)
+    osk = O.SecretKey(OP, 9)
+    ock = O.CloudKey(osk, 10)
+    os.makedirs(directory, exist_ok=True)
+    sk = T.key.SecretKey(P, osk.s0.copy(), osk.s1.copy())
+    ck = T.cloudkey.CloudKey(P, ock.offset, ock.testvec.reshape(2, OP.N), ock.ksk, ock.bsk_fft)
+    open(os.path.join(directory, "secret.tfhb"), "wb").write(T.wire.dumps_secret_key(sk))
+    open(os.path.join(directory, "cloud.tfhb"), "wb").write(T.wire.dumps_cloud_key(ck))
+    impl = OracleImpl(O, OP, ock)
+    N, n = OP.N, OP.n
+    rng = np.random.default_rng(3)
+    v = {}
+    v["polp"] = (np.arange(N, dtype=np.uint64) * 12345 % (1 << 32)).astype(np.uint32)
+    v["polf"] = impl.to_fourier(v["polp"])
+    rows = np.array([0, n - 1], dtype=np.uint32)
+    c0 = rng.integers(0, 1 << 32, (4, 2 * N), dtype=np.uint64).astype(np.uint32)
+    c1 = rng.integers(0, 1 << 32, (4, 2 * N), dtype=np.uint64).astype(np.uint32)
+    v["erow"], v["ec0"], v["ec1"] = rows, c0, c1
+    v["eout"] = np.concatenate([impl.external_product(int(r), c1[2 * k:2 * k + 2]) for k, r in enumerate(rows)])
+    v["cout"] = np.concatenate([impl.cmux(int(r), c0[2 * k:2 * k + 2], c1[2 * k:2 * k + 2]) for k, r in enumerate(rows)])
+    if name in EXACT:
+        bits = np.arange(count, dtype=np.uint32) & 7
+        a, b, c = osk.encrypt_bool(bits & 1, 21), osk.encrypt_bool((bits >> 1) & 1, 22), osk.encrypt_bool((bits >> 2) & 1, 23)
+        v["bits"], v["ina"], v["inb"], v["inc"] = bits, a, b, c
+        for tag, op in GATE_TAGS.items():
+            v[tag] = impl.gate(op, a, b)
+        v["MUX"], v["NOT"], v["COPY"] = impl.gate("MUX", a, b, c), impl.gate("NOT", a, None), impl.gate("COPY", a, None)
+        v["rot"], v["boot"] = impl.blind_rotate(a), impl.bootstrap(a)
+    else:
+        m = {"uint1": 2, "uint2": 4, "uint3": 8, "uint4": 16, "uint5": 32}[name]
+        msgs = np.array([(i * (m - 1) // count) % m for i in range(count - 1)] + [m - 1], dtype=np.uint32)
+        ct = osk.encrypt_message(msgs.astype(np.int32), m, 31)
+        fs = [lambda x: x, lambda x: (m - 1) - x, lambda x: x % (m // 2) if m > 2 else x]
+        luts = np.stack([O.gen_lut(OP, m, f) for f in fs])
+        v["msgs"], v["mmod"], v["ct"], v["luts"] = msgs, np.array([m], dtype=np.uint32), ct, luts
+        for k in range(3):
+            v["rot%d" % k], v["pbs%d" % k] = impl.blind_rotate(ct, luts[k]), impl.bootstrap(ct, luts[k])
+    open(os.path.join(directory, "vectors.tfhb"), "wb").write(T.wire.dumps_bundle(P, v))
+
+
+@pytest.fixture(scope="module")
+def T():
+    return importlib.import_module("go-tfhe_b200")
+
+
+def test_golden_kit_self_check(T, O, tmp_path):
+    """Loader + checker on files of the mkgolden layout (made by the oracle here): pass as written, fail on one flipped word."""
+    d = str(tmp_path / "80")
+    write_set_with_oracle(T, O, d, "80", count=4)
+    OP, osk, ock, ck, vec = load_set(T, O, d, "80")
+    assert check_vectors(OracleImpl(O, OP, ock), "80", OP, osk, vec, 0.0) >= 20
+    vec["XOR"] = vec["XOR"].copy()
+    vec["XOR"][5] ^= 1
+    with pytest.raises(AssertionError):
+        check_vectors(OracleImpl(O, OP, ock), "80", OP, osk, vec, 0.0)
+
+
+@pytest.mark.parametrize("name", present_sets() or ["<none>"])
+def test_oracle_matches_go_reference(T, O, name):
+    if name == "<none>":
+        pytest.skip("NO GO GOLDEN VECTORS under tests/golden/go: ciphertext-level parity to the Go reference is UNPINNED. "
+                    "Run go/cmd/mkgolden where a Go toolchain exists (see its header) and drop the files in.")
+    OP, osk, ock, ck, vec = load_set(T, O, os.path.join(GOLD, name), name)
+    # Go's math.Sincos and libm's sincos may differ in the last bit of a twiddle: 1e-13 relative on the spectrum
+    n = check_vectors(OracleImpl(O, OP, ock), name, OP, osk, vec, 1e-13)
+    print("oracle == Go reference on %d checks (%s)" % (n, name))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", present_sets() or ["<none>"])
+def test_gpu_matches_go_reference(T, O, name):
+    if name == "<none>":
+        pytest.skip("NO GO GOLDEN VECTORS under tests/golden/go: GPU-vs-Go ciphertext parity is UNPINNED "
+                    "(GPU == oracle is tested in tests/test_gpu_parity.py). See go/cmd/mkgolden.")
+    OP, osk, ock, ck, vec = load_set(T, O, os.path.join(GOLD, name), name)
+    impl = GpuImpl(T, name, ck)
+    try:
+        n = check_vectors(impl, name, OP, osk, vec, 1e-11)  # different butterfly rounding in the forward transform (stated)
+        print("GPU == Go reference on %d checks (%s)" % (n, name))
+    finally:
+        impl.close()
+
+
+@pytest.mark.gpu
+def test_gpu_passes_the_kit_on_oracle_made_files(T, O, tmp_path):
+    """The GPU through the very same loader + checker, on oracle-made files (exact set and a Uint set)."""
+    for name in ("80", "uint2"):
+        d = str(tmp_path / name)
+        write_set_with_oracle(T, O, d, name, count=4)
+        OP, osk, ock, ck, vec = load_set(T, O, d, name)
+        impl = GpuImpl(T, name, ck)
+        try:
+            assert check_vectors(impl, name, OP, osk, vec, 1e-11) >= 10
+        finally:
+            impl.close()
