@@ -227,17 +227,24 @@ def config_c4(T, np, device, count=2048, reps=3):
         luts = np.stack([T.lut.NewGenerator(m, P).GenLookUpTable(f).Poly for f in fs]).reshape(3, -1)
         sel = rng.integers(0, 3, count)
         per = np.ascontiguousarray(luts[sel])
-        ctx.bootstrap_batch(ct, per)
+        out_per = ctx.bootstrap_batch(ct, per)              # a full 16 KiB LUT per ciphertext crosses the bus
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.bootstrap_batch(ct, per)
+        dt_per = (time.perf_counter() - t0) / reps
+        ctx.bootstrap_batch_indexed(ct, luts, sel)          # the three LUTs once + an index per ciphertext
         ctx.set_timing(True)
         ctx.collect_timing()
         t0 = time.perf_counter()
         for _ in range(reps):
-            out = ctx.bootstrap_batch(ct, per)
+            out = ctx.bootstrap_batch_indexed(ct, luts, sel)
         dt = (time.perf_counter() - t0) / reps
         tm = ctx.collect_timing()
         want = np.array([fs[k](int(v)) for k, v in zip(sel, msgs)])
-        return {"workload": "programmable bootstrap, Uint5 (n=1071, N=2048, msgMod 32), batch %d, one LUT per ciphertext, host buffers" % count,
+        return {"workload": "programmable bootstrap, Uint5 (n=1071, N=2048, msgMod 32), batch %d, 3 LUTs chosen per ciphertext "
+                            "(tfhe_bootstrap_batch_indexed), host buffers" % count,
                 "bootstraps_per_s": count / dt, "seconds": dt,
+                "bootstraps_per_s_lut_per_ciphertext": count / dt_per, "same_words_both_ways": bool(np.array_equal(out, out_per)),
                 "blind_rotate_ms": tm["blind_rotate_ms"] / max(tm["blind_rotate_launches"], 1),
                 "key_switch_ms": tm["key_switch_ms"] / max(tm["key_switch_launches"], 1),
                 "device_keygen_s": keygen_s,

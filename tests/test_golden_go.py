@@ -8,7 +8,7 @@ section 2).  To keep the checker itself honest, test_golden_kit_self_check build
 temporary directory, runs the very same comparison on them, and shows that a single flipped output word is caught.
 
 Bar (the same for oracle-vs-Go and GPU-vs-Go): bit-exact torus words on the 80/110/128-bit sets for every vector; on the
-Uint sets decoded messages exact and phases within the per-set tolerance of tests/test_gpu_parity.py::UINT_TOL."""
+Uint sets decoded messages exact and phases within the per-set tolerance of tests/tolerances.py."""
 import glob
 import importlib
 import os
@@ -21,10 +21,7 @@ GOLD = os.path.join(ROOT, "tests", "golden", "go")
 EXACT = {"80", "110", "128"}
 GATE_TAGS = {"NAND": "NAND", "AND": "AND", "OR": "OR", "XOR": "XOR", "XNOR": "XNOR", "NOR": "NOR", "ANNY": "ANDNY",
              "ANYN": "ANDYN", "ORNY": "ORNY", "ORYN": "ORYN"}
-# phase tolerance (torus LSB) after blind rotate / after key switch for the sets whose f64 sums are not exact; ~4x the
-# worst case observed GPU-vs-oracle in round 1 (tests/test_gpu_parity.py prints the observed values)
-UINT_TOL = {"uint1": (1 << 4, 1 << 22), "uint2": (1 << 23, 1 << 25), "uint3": (1 << 22, 1 << 24), "uint4": (1 << 22, 1 << 23),
-            "uint5": (1 << 22, 1 << 22)}
+from tolerances import UINT_PHASE_TOL as UINT_TOL  # per-set phase tolerances, ~4x the observed GPU-vs-oracle worst case
 
 
 def present_sets():

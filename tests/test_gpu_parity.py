@@ -6,6 +6,8 @@ import importlib
 import numpy as np
 import pytest
 
+from tolerances import UINT_PHASE_TOL
+
 pytestmark = pytest.mark.gpu
 
 TRUTH = {"NAND": [1, 1, 1, 0], "AND": [0, 0, 0, 1], "OR": [0, 1, 1, 1], "XOR": [0, 1, 1, 0], "XNOR": [1, 0, 0, 1],
@@ -254,22 +256,18 @@ def _centered(d):
 
 @pytest.mark.parametrize("name,m", [("uint1", 2), ("uint2", 4), ("uint3", 8), ("uint4", 16), ("uint5", 32)])
 def test_pbs_uint_sets_within_tolerance(O, gpu, name, m):  # row a19; params/uint_params_test.go:61-126
-    """With L <= 2 and a 2^10..2^23 gadget base the reference's own f64 sums reach 2^52..2^64, so
+    """With L = 1 and a 2^18..2^23 gadget base the reference's own f64 sums reach 2^58..2^64, so
     its rounded external product depends on summation order and GPU == oracle only up to a tolerance.  Torus WORDS
     cannot be compared there at all: one LSB of difference that crosses a digit boundary of the next decomposition
     swaps in a different (uniformly random) key-row mask, so ciphertexts diverge while their PHASES stay close.
-    Stated tolerances (phases, in torus LSB):
-      * after blind rotate + sample extract, under the ring key: |delta| <= 2^24 (2^-8 of the torus).  Once the masks
-        have diverged, the truncating gadget decomposition (L*bgbit < 32 bits kept) contributes independent
-        truncation noise to each side: ~2^21 at Uint2 (14 bits dropped, n=687 steps), less elsewhere;
-      * after key switching: the two (now unrelated) masks are rounded independently to basebit*t bits, so the
-        phases differ by two independent key-switch rounding noises: |delta| < min(2^26, (2^31/m)/4);
-      * decoded messages identical, for both implementations, for identity / complement / modulo."""
+    Stated tolerances: per parameter set, ~4x the worst case observed on a B200 — tests/tolerances.py holds the table and
+    the observations.  Uint1 (L = 2, Bg = 2^10) is exact: words must be equal.  Decoded messages identical everywhere."""
     P, sk, ck, ctx = gpu(name)
     ev = O.Evaluator(P.N)
     xs = list(range(m)) if m <= 8 else [0, 1, 2, m // 2, m - 3, m - 2, m - 1]
     ct = sk.encrypt_message(xs, m, 71)
-    tol_ks = min(1 << 26, ((1 << 31) // m) // 4)
+    tol_br, tol_ks = UINT_PHASE_TOL[name]
+    assert tol_ks < ((1 << 31) // m) // 2   # inside the decode margin of the set
     for f in (lambda x: x, lambda x: (m - 1) - x, lambda x: x % (m // 2) if m > 2 else x):
         lut = O.gen_lut(P, m, f)
         rot = ctx.blind_rotate_batch(ct, lut).reshape(len(xs), -1)
@@ -281,11 +279,13 @@ def test_pbs_uint_sets_within_tolerance(O, gpu, name, m):  # row a19; params/uin
         got = ctx.bootstrap_batch(ct, lut)
         want = O.bootstrap_batch(ck, ct, lut)
         d2 = np.abs(_centered(sk.phase(got).astype(np.int64) - sk.phase(want).astype(np.int64))).max()
-        print(name, "max |delta phase|: after blind rotate", d1, " after key switch", d2, " tol", 1 << 24, tol_ks)
-        assert d1 <= (1 << 24)
+        print(name, "max |delta phase|: after blind rotate", d1, " after key switch", d2, " tol", tol_br, tol_ks)
+        assert d1 <= tol_br
+        if tol_br == 0:
+            assert np.array_equal(rot, np.stack([ev.blind_rotate(P, c, lut, ck.bsk_fft, ck.offset) for c in ct])) and np.array_equal(got, want)
         assert list(sk.decrypt_message(got, m)) == [f(x) for x in xs]
         assert list(sk.decrypt_message(want, m)) == [f(x) for x in xs]
-        assert d2 < tol_ks
+        assert d2 <= tol_ks
 
 
 def test_full_size_batch_properties(T, gpu):
