@@ -166,3 +166,44 @@ def test_nonzero_k0_rows_of_an_uploaded_key_are_ignored(T, O, env):
     finally:
         ctx.set_key_switch_variant("auto")
         other.close()
+
+
+def test_c5_mixed_gates_sharded_by_index_reduced(T, O, keyset):
+    """BASELINE.json configs[4] at reduced size (tools/bench_c5_multi.py and bench.py's c5 leg run it at 2^20): 2^12
+    mixed AND/OR/XOR/MUX gate-ops at 128-bit whose operands are gathered from a ciphertext pool, cut into contiguous
+    index ranges exactly as the ranks of a torchrun job cut them (sharding.shard_bounds), each range one host-buffer call.
+    The concatenation must be the words of the single call and of the multi-device context, every output must decrypt
+    to the plaintext gate, and a sample of gate-ops must equal the oracle word for word."""
+    P, sk, ck = keyset("128")
+    ctx = T.Context(T.params.get("128"), 0)
+    multi = T.Context(T.params.get("128"), devices="all")
+    try:
+        ctx.load_cloudkey(ck.offset, ck.bsk_fft, ck.ksk, ck.testvec)
+        multi.load_cloudkey(ck.offset, ck.bsk_fft, ck.ksk, ck.testvec)
+        total, pool = 1 << 12, 256
+        rng = np.random.default_rng(1)
+        bits = rng.integers(0, 2, pool).astype(np.uint8)
+        cts = sk.encrypt_bool(bits, 5)
+        ia, ib, ic = (rng.integers(0, pool, total) for _ in range(3))
+        ops = rng.integers(0, 4, total)
+        names = ("AND", "OR", "XOR", "MUX")
+        opcodes = np.array([T.OPCODES[o] for o in names], dtype=np.uint8)[ops]
+        whole = ctx.gate_batch(opcodes, cts[ia], cts[ib], cts[ic])
+        for world in (2, 3, 8):
+            parts = []
+            for lo, hi in T.sharding.shard_bounds(total, world):
+                parts.append(ctx.gate_batch(opcodes[lo:hi], cts[ia[lo:hi]], cts[ib[lo:hi]], cts[ic[lo:hi]]))
+            assert np.array_equal(np.concatenate(parts), whole), world
+        assert np.array_equal(multi.gate_batch(opcodes, cts[ia], cts[ib], cts[ic]), whole)
+        A, B, C = bits[ia], bits[ib], bits[ic]
+        want = np.select([ops == 0, ops == 1, ops == 2], [A & B, A | B, A ^ B], np.where(A == 1, B, C))
+        assert np.array_equal(sk.decrypt_bool(whole), want)
+        for g in (0, 1, 2, 3, total - 1):
+            if ops[g] == 3:
+                ref = O.mux(ck, cts[ia[g]][None], cts[ib[g]][None], cts[ic[g]][None])[0]
+            else:
+                ref = O.gate_batch(ck, names[ops[g]], cts[ia[g]], cts[ib[g]])[0]
+            assert np.array_equal(whole[g], ref), g
+    finally:
+        ctx.close()
+        multi.close()
