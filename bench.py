@@ -296,6 +296,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")   # host-side waits (see the one-call multi-device leg)
 
     T = importlib.import_module("go-tfhe_b200")
     P = T.params.get(PARAMS)
@@ -454,7 +455,7 @@ def main():
             configs[name] = c
         configs["c3_adder"]["vs_c2_rate"] = configs["c3_adder"]["bootstraps_per_s"] / (count / (dev_ms / args.steps * 1e-3))
         # the same c5 job once more through ONE multi-device context in ONE process (rank 0; the other ranks idle at the
-        # barrier): tfhe_ctx_create_multi shards a single tfhe_gate_batch call over every GPU behind the C ABI
+        # CPU-side barrier): tfhe_ctx_create_multi shards a single tfhe_gate_batch call over every GPU behind the C ABI
         barrier()
         if world > 1 and rank == 0:
             multi = T.Context(P, devices=list(range(world)))
@@ -473,6 +474,8 @@ def main():
                     "correct": bool(np.array_equal(T.tlwe.DecryptBool(out5, sk), want5))}
             finally:
                 multi.close()
+        if world > 1:   # the idle ranks wait on the CPU (gloo): a spinning NCCL barrier kernel would time-slice GPUs 1.. with the job
+            dist.barrier(group=cpu_group)
         barrier()
 
     # --- reduce over ranks: max time --------------------------------------------------------------------------

@@ -46,6 +46,9 @@
 #ifndef TFHE_BR_PF_L1
 #define TFHE_BR_PF_L1 0         // d > 0: prefetch.global.L1 of the key rows d digits ahead of the MAC that uses them (2 lines per thread).  +0.5 % with the round-1 kernel, -3.7 % with the persistent work-item kernel (97.1 k -> 100.7 k gates/s without it): off
 #endif
+#ifndef TFHE_BR_TW_CONST
+#define TFHE_BR_TW_CONST 0      // 1: twiddles of the passes with <= 8 blocks (pass 1) come from the constant bank (LDC, not an LSU instruction) instead of L1
+#endif
 #ifndef TFHE_BR_KO
 #define TFHE_BR_KO 0            // TIMING EXPERIMENTS ONLY (wrong results): bit 0 = no exchanges, bit 1 = no key loads, bit 2 = no barrier in exchanges
 #endif
@@ -71,6 +74,9 @@ __host__ __device__ constexpr int br_nbuf(int logn) { return br_warp_ex(logn) ? 
 namespace tfhe {
 
 struct Tw4 { double2 s[4]; };  // twiddles of one radix-8 block: S(m,i), S(2m,2i), S(4m,4i), S(4m,4i+2)
+#if TFHE_BR_TW_CONST
+__constant__ Tw4 c_tw_pass1[3][8];  // [LOGM - 8][block] : pass-1 twiddles of the M = 256, 512, 1024 transforms
+#endif
 
 struct BrArgs {
   const uint32_t* ct_in;    // [count][n+1]  (already linearly combined)
@@ -387,6 +393,13 @@ struct Fft {
       double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
       radix8_fwd<G::nstages(K)>(x, s0, s1, s2, s3);
     } else {
+#if TFHE_BR_TW_CONST
+      if constexpr (K == 1) {
+        const Tw4& e = c_tw_pass1[LOGM - 8][G::block_of(K, tau)];
+        radix8_fwd<3>(x, e.s[0], e.s[1], e.s[2], e.s[3]);
+        return;
+      }
+#endif
       const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
       double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
       radix8_fwd<3>(x, s0, s1, s2, s3);
@@ -403,6 +416,13 @@ struct Fft {
       double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
       radix8_inv<G::nstages(K)>(x, s0, s1, s2, s3);
     } else {
+#if TFHE_BR_TW_CONST
+      if constexpr (K == 1) {
+        const Tw4& e = c_tw_pass1[LOGM - 8][G::block_of(K, tau)];
+        radix8_inv<3>(x, e.s[0], e.s[1], e.s[2], e.s[3]);
+        return;
+      }
+#endif
       const Tw4* e = tab + G::tab_off(K) + G::block_of(K, tau);
       double2 s0 = __ldg(&e->s[0]), s1 = __ldg(&e->s[1]), s2 = __ldg(&e->s[2]), s3 = __ldg(&e->s[3]);
       radix8_inv<3>(x, s0, s1, s2, s3);

@@ -686,6 +686,10 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
     case 11: build_twiddles<10>(c->tw0, tab); break;
     default: tfhe_ctx_destroy(c); return fail(nullptr, TFHE_ERR_ARG, "unsupported N");
   }
+#if TFHE_BR_TW_CONST
+  if (tab.size() >= 8 && (e = cudaMemcpyToSymbol(c_tw_pass1, tab.data(), 8 * sizeof(Tw4), (size_t)(c->logN - 9) * 8 * sizeof(Tw4))) != cudaSuccess)
+    return bail("cudaMemcpyToSymbol(twiddles)", e);
+#endif
   if ((e = cudaMalloc(&c->d_tw, tab.size() * sizeof(Tw4))) != cudaSuccess) return bail("cudaMalloc(twiddles)", e);
   if ((e = cudaMemcpy(c->d_tw, tab.data(), tab.size() * sizeof(Tw4), cudaMemcpyHostToDevice)) != cudaSuccess)
     return bail("cudaMemcpy(twiddles)", e);
