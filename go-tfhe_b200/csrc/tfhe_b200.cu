@@ -34,6 +34,7 @@
 #include "blind_rotate_lat.cuh"
 #include "lwe_kernels.cuh"
 #include "key_switch_mma.cuh"
+#include "key_switch_tile.cuh"
 #include "keygen.cuh"
 #include "fp64_probe.cuh"
 
@@ -92,12 +93,14 @@ struct tfhe_ctx {
   uint8_t* d_ksk_bytes = nullptr;  // [4*ksk_stride][ks_K]
   long long ks_K = 0;              // N * t * (base - 1); 0 = path unavailable for this parameter set
   CUtensorMap ks_mapB{};
-  int ks_variant = 0;              // 0 = auto, 1 = row gather (key_switch_kernel), 2 = tensor-core contraction
+  CUtensorMap ks_tile_map{};      // the repacked key-switching key as [rows][stride] u32, box = base rows x 64 words (key_switch_tile.cuh)
+  bool ks_tile_ok = false;
+  int ks_variant = 0;              // 0 = auto, 1 = row gather (key_switch_kernel), 2 = tensor-core contraction, 3 = shared-memory tiles (ks_tile_kernel)
   int mux_mode = 0;                // 0 = the reference's three bootstraps per MUX, 1 = two blind rotations + one key switch
   // proxy re-encryption key (proxyreenc.ProxyReencryptionKey.KeyEncryptions): [n*t*base][stride] rows under the target key
   uint32_t* d_reenc = nullptr;
   int reenc_stride = 0, reenc_basebit = 0, reenc_t = 0;
-  DevBuf ks_sel;                   // selection matrix of the current chunk
+  DevBuf ks_sel;                   // selection matrix of the current chunk (tensor-core path) / digit matrix (tile path)
   Tw4 tw0{};
   cudaStream_t stream = nullptr;  // used by the host-buffer API (compute)
   cudaStream_t s_in = nullptr, s_out = nullptr;  // copy-in / copy-out streams of the pipelined host-buffer calls
@@ -481,6 +484,21 @@ int make_ks_map(tfhe_ctx* c, CUtensorMap* m, const void* base, long long K, long
   return 0;
 }
 
+// [rows][stride] u32 matrix, box = box_rows x box_words, no swizzle, out-of-range columns read as zeros
+int make_u32_map(tfhe_ctx* c, CUtensorMap* m, const void* base, long long stride_words, long long rows, int box_words, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(c, TFHE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {(cuuint64_t)stride_words, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)stride_words * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)box_words, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(c, TFHE_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
 // Tensor-core path: chunks of <= 8192 ciphertexts (selection matrix <= K * 8192 bytes).
 int launch_key_switch_mma(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s,
                           const GateDesc* out_gates, long long instances) {
@@ -521,6 +539,34 @@ int launch_key_switch_mma(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, ui
   return 0;
 }
 
+int launch_key_switch_tile(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s,
+                           const GateDesc* out_gates, long long instances) {
+  const auto& P = c->P;
+  const int base = 1 << P.basebit, K = P.N * P.iks_t;
+  const int64_t ct_tiles = (count + KST_CT - 1) / KST_CT, cpad = ct_tiles * KST_CT;
+  const int col_tiles = (P.n + 1 + KST_COLS - 1) / KST_COLS;
+  CK(c, c->ks_sel.reserve((size_t)K * cpad));
+  ks_digits_kernel<<<dim3((unsigned)ct_tiles, (unsigned)(P.N / 8)), 256, 0, s>>>(d_lwe1, c->ks_sel.as<uint8_t>(), d_out, count, cpad, P.N, P.n,
+                                                                               P.basebit, P.iks_t, out_gates, instances);
+  c->launches++;
+  // split the (i, j) pairs of a tile over `ksplit` blocks so that the blocks fill whole rounds of the resident slots
+  // (2 per SM); each block pays ~24 pairs' worth of prologue + epilogue
+  const int64_t tiles = ct_tiles * col_tiles, slots = 2 * (int64_t)c->sm_count;
+  int best = 1;
+  double best_cost = 1e300;
+  for (int ks = 1; ks <= 64 && ks * 64 <= K; ks++) {
+    const double rounds = std::ceil((double)tiles * ks / slots);
+    const double cost = rounds * ((double)K / ks + 24.0);
+    if (cost < best_cost) { best_cost = cost; best = ks; }
+  }
+  auto kern = base == 64 ? ks_tile_kernel<64> : base == 32 ? ks_tile_kernel<32> : ks_tile_kernel<16>;
+  kern<<<(unsigned)(tiles * best), KST_THREADS, kst_smem_bytes(base), s>>>(c->ks_tile_map, c->ks_sel.as<uint8_t>(), d_out, K, count, cpad, P.n,
+                                                                       col_tiles, best, (int)ct_tiles, out_gates, instances);
+  c->launches++;
+  CK(c, cudaGetLastError());
+  return 0;
+}
+
 int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32_t* d_out, cudaStream_t s,
                       const GateDesc* out_gates = nullptr, long long instances = 1) {
   if (count == 0) return 0;
@@ -529,6 +575,11 @@ int launch_key_switch(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, uint32
   // 6.43 ms — the contraction wins at every batch size (a lone gather block streams its 19 MB at one SM's bandwidth)
   if (c->ks_K && (c->ks_variant == 2 || c->ks_variant == 0))
     return launch_key_switch_mma(c, count, d_lwe1, d_out, s, out_gates, instances);
+  // large-base sets (Uint2-5), a tile's worth of ciphertexts or more: shared-memory tiles (key_switch_tile.cuh).  One tile of
+  // 256 ciphertexts costs what ~140 gathered ciphertexts cost (Uint5), so the switch-over sits below a full tile.
+  if (c->ks_tile_ok && (c->ks_variant == 3 || (c->ks_variant == 0 && count >= 160)))
+    return launch_key_switch_tile(c, count, d_lwe1, d_out, s, out_gates, instances);
+  if (c->ks_variant == 3) return fail(c, TFHE_ERR_STATE, "tiled key switch is for the basebit 4..6 parameter sets");
   const size_t sm = (size_t)c->P.N * c->P.iks_t * sizeof(uint32_t);
   if (sm > 128 * 1024) return fail(c, TFHE_ERR_ARG, "N * iks_t too large for the key-switch kernel");
   // one thread per 16-byte column of a key row, so that the row loop runs once (n = 1071: 268 columns -> 288 threads,
@@ -767,6 +818,10 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
     return bail("cudaFuncSetAttribute(ks_mma)", e);
   if ((e = cudaFuncSetAttribute(ks_onehot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)) != cudaSuccess)
     return bail("cudaFuncSetAttribute(ks_onehot)", e);
+  if (P.basebit >= 4 && P.basebit <= 6 &&
+      (e = cudaFuncSetAttribute(P.basebit == 6 ? ks_tile_kernel<64> : P.basebit == 5 ? ks_tile_kernel<32> : ks_tile_kernel<16>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kst_smem_bytes(1 << P.basebit))) != cudaSuccess)
+    return bail("cudaFuncSetAttribute(ks_tile)", e);
   if ((e = cudaFuncSetAttribute(key_switch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 128 * 1024)) != cudaSuccess)  // a limit shared by every context of the process
     return bail("cudaFuncSetAttribute(key_switch)", e);
@@ -879,6 +934,12 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
     c->launches++;
     CK(c, cudaGetLastError());
     c->has_ksk = true;
+    c->ks_tile_ok = false;
+    if (P.basebit >= 4 && P.basebit <= 6 && encode_tiled_fn()) {
+      int rcm = make_u32_map(c, &c->ks_tile_map, c->d_ksk, c->ksk_stride, (long long)rows, KST_COLS, 1 << P.basebit);
+      if (rcm) return rcm;
+      c->ks_tile_ok = true;
+    }
     // byte planes for the tensor-core key switch: only where the dense product is cheap (base - 1 = 3 rows per digit)
     const long long K = (long long)P.N * P.iks_t * ((1 << P.basebit) - 1);
     if (P.basebit == 2 && K % KSM_BK == 0 && K <= 160 * 1024 && encode_tiled_fn()) {
@@ -1676,7 +1737,7 @@ int64_t tfhe_ctx_kernel_launches(const tfhe_ctx* c) {
 
 int tfhe_ctx_set_key_switch_variant(tfhe_ctx* c, int variant) {
   GROUP_FORWARD(c, tfhe_ctx_set_key_switch_variant(kid, variant));
-  if (!c || variant < 0 || variant > 2) return fail(c, TFHE_ERR_ARG, "key-switch variant must be 0 (auto), 1 (gather) or 2 (tensor core)");
+  if (!c || variant < 0 || variant > 3) return fail(c, TFHE_ERR_ARG, "key-switch variant must be 0 (auto), 1 (gather), 2 (tensor core) or 3 (shared-memory tiles)");
   c->ks_variant = variant;
   return TFHE_OK;
 }

@@ -273,8 +273,9 @@ class Context:
         self._ck(self.lib.tfhe_ctx_set_blind_rotate_chunk_steps(self.h, int(steps)), "tfhe_ctx_set_blind_rotate_chunk_steps")
 
     def set_key_switch_variant(self, variant):
-        """'auto' (default) | 'gather' | 'mma' — row gather out of L2 or one tensor-core contraction; results are identical."""
-        v = {"auto": 0, "gather": 1, "mma": 2}[variant] if isinstance(variant, str) else int(variant)
+        """'auto' (default) | 'gather' | 'mma' | 'tile' — row gather out of L2, one tensor-core contraction (basebit = 2 sets) or
+        shared-memory tiles of 256 ciphertexts (basebit >= 4 sets); results are identical."""
+        v = {"auto": 0, "gather": 1, "mma": 2, "tile": 3}[variant] if isinstance(variant, str) else int(variant)
         self._ck(self.lib.tfhe_ctx_set_key_switch_variant(self.h, v), "tfhe_ctx_set_key_switch_variant")
 
     def set_timing(self, enable=True):

@@ -234,10 +234,12 @@ int tfhe_ctx_set_blind_rotate_chunk_steps(tfhe_ctx* ctx, int steps);
  * chunk k+1 (in) and k-1 (out) overlap the kernels of chunk k on separate streams, and device staging stays bounded by
  * two chunks whatever the batch size.  Results do not depend on it. */
 int tfhe_ctx_set_pipeline_chunk(tfhe_ctx* ctx, int64_t rows);
-/* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default: the contraction wherever it exists), 1 = one block per
+/* Selects how IdentityKeySwitching (trgsw/keyswitch.go:10-37) is evaluated: 0 = automatic (default: the contraction wherever it exists, tiles for large bases and batches), 1 = one block per
  * ciphertext gathering its N*t*(1-1/base) key rows out of L2, 2 = the whole batch as one exact u8 x u8 -> s32
  * contraction on the tensor cores (tcgen05.mma kind::i8 over the byte planes of the key; basebit = 2 parameter sets
- * only).  Both are bit-identical: additions mod 2^32 commute. */
+ * only), 3 = shared-memory tiles for the basebit >= 4 sets (Uint2-5): a block owns 256 ciphertexts x 64 output words and
+ * stages the `base` candidate rows of each (i, j) once for all of them (automatic from 160 ciphertexts on).  All are
+ * bit-identical: additions mod 2^32 commute. */
 int tfhe_ctx_set_key_switch_variant(tfhe_ctx* ctx, int variant);
 /* Per-stage device timing for bench.py's roofline: when enabled, every bootstrap batch records CUDA events on
  * its launching stream around the blind-rotate kernel and the key-switch kernel.  tfhe_ctx_collect_timing waits

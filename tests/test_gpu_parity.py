@@ -162,6 +162,30 @@ def test_key_switch_tensor_core_bit_exact(O, gpu, name, count):  # row a17 as on
         assert np.array_equal(got[i], O.key_switch(P, ext[i], ck.ksk))
 
 
+@pytest.mark.parametrize("name,count", [("uint2", 7), ("uint2", 256), ("uint2", 700), ("uint4", 300), ("uint5", 161), ("uint5", 513)])
+def test_key_switch_tiles_bit_exact(O, gpu, name, count):  # row a17 for the large-base sets (base 16 / 32 / 64)
+    """ks_tile_kernel (256 ciphertexts x 64 words per block, candidate rows staged in shared memory, K split over blocks with
+    atomic adds) must give the words of the row gather and of trgsw/keyswitch.go:10-37: partial ciphertext tiles, the
+    overhanging last column tile (n + 1 not a multiple of 64) and all three bases are exercised."""
+    P, sk, ck, ctx = gpu(name)
+    rng = np.random.default_rng(2000 + count)
+    ext = rng.integers(0, 1 << 32, (count, P.N + 1), dtype=np.uint64).astype(np.uint32)
+    ext[0, : P.N] = 0                      # only k = 0 rows: nothing is subtracted
+    ext[min(1, count - 1), : P.N] = 0xFFFFFFFF
+    try:
+        ctx.set_key_switch_variant("gather")
+        ref = ctx.key_switch_batch(ext)
+        ctx.set_key_switch_variant("tile")
+        got = ctx.key_switch_batch(ext)
+    finally:
+        ctx.set_key_switch_variant("auto")
+    assert np.array_equal(got, ref)
+    assert np.array_equal(ctx.key_switch_batch(ext), ref)      # whatever "auto" picks at this count
+    assert np.array_equal(got[0, : P.n], np.zeros(P.n, dtype=np.uint32)) and got[0, P.n] == ext[0, P.N]
+    for i in (1, count - 1):
+        assert np.array_equal(got[i], O.key_switch(P, ext[i], ck.ksk))
+
+
 @pytest.mark.parametrize("name", ["80", "110", "128"])
 def test_bootstrap_bit_exact_and_decrypts(O, gpu, name):  # row a18
     P, sk, ck, ctx = gpu(name)

@@ -1,4 +1,4 @@
-"""A few programmable bootstraps of one parameter set at one batch size (ncu target): python tools/pbs_run.py <set> <count> [reps]"""
+"""A few programmable bootstraps of one parameter set at one batch size (ncu target): python tools/pbs_run.py <set> <count> [reps] [auto|gather|tile]"""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,7 +13,10 @@ ctx.generate_cloudkey(sk.KeyLv0, sk.KeyLv1, seed=2, with_ksk=True, export=False)
 msgs = np.arange(count) % m
 ct = T.tlwe.EncryptLWEMessage(msgs, m, sk, 3)
 lut = T.lut.NewGenerator(m, P).GenLookUpTable(lambda v: (m - 1) - v).Poly.reshape(1, -1)
+if len(sys.argv) > 4:
+    ctx.set_key_switch_variant(sys.argv[4])
 ctx.set_timing(True)
 for _ in range(reps):
     out = ctx.bootstrap_batch(ct, lut)
-print(name, count, "correct", bool(np.array_equal(T.tlwe.DecryptLWEMessage(out, m, sk), (m - 1) - msgs)), ctx.collect_timing())
+    tm = ctx.collect_timing()
+print(name, count, "correct", bool(np.array_equal(T.tlwe.DecryptLWEMessage(out, m, sk), (m - 1) - msgs)), tm)
