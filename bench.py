@@ -441,21 +441,32 @@ def main():
             share = "all 2^%d gate-ops, sharded by index over %d ranks" % (args.c5_log2, world)
         lo, hi = T.sharding.shard_bounds(total, world)[rank]
         ops5, a5, b5, c5, want5, nboot5 = c5_inputs(T, np, sk, total, lo, hi)
-        ctx.gate_batch(ops5[:2048], a5[:2048], b5[:2048], c5[:2048])
+        # pinned host buffers through the C ABI (as the headline e2e); the warm-up call is long enough (2.5 pipeline chunks)
+        # to size both staging slots, so the timed call measures the steady state of a serving process, not cudaMalloc
+        a5p, b5p, c5p = (torch.from_numpy(x).pin_memory() for x in (a5, b5, c5))
+        out5p = torch.empty_like(a5p).pin_memory()
+        ops5 = np.ascontiguousarray(ops5, dtype=np.uint8)
+
+        def c5_call(cnt):
+            rc = ctx.lib.tfhe_gate_batch(ctx.h, cnt, ops5.ctypes.data, cnt, a5p.data_ptr(), b5p.data_ptr(), c5p.data_ptr(), out5p.data_ptr())
+            if rc:
+                raise RuntimeError("tfhe_gate_batch failed (%d)" % rc)
+        c5_call(min(len(ops5), 40960))
         barrier()
         t0 = time.perf_counter()
-        out5 = ctx.gate_batch(ops5, a5, b5, c5)
+        c5_call(len(ops5))
         torch.cuda.synchronize()
         t5 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        out5 = out5p.numpy()
         ok5 = torch.tensor([int(np.array_equal(T.tlwe.DecryptBool(out5, sk), want5))], dtype=torch.int64, device=dev)
         if world > 1:
             dist.all_reduce(t5, op=dist.ReduceOp.MAX)
             dist.all_reduce(ok5, op=dist.ReduceOp.MIN)
-        configs["c5_mixed"] = {"workload": "mixed AND/OR/XOR/MUX (uniform), 128-bit, %s; one tfhe_gate_batch call per rank, host buffers" % share,
+        configs["c5_mixed"] = {"workload": "mixed AND/OR/XOR/MUX (uniform), 128-bit, %s; one tfhe_gate_batch call per rank, pinned host buffers" % share,
                                "scaling": "strong" if world > 1 else "per-GPU share", "gate_ops": total, "bootstraps": nboot5,
                                "seconds_max_over_ranks": float(t5.item()), "gate_ops_per_s": total / float(t5.item()),
                                "bootstraps_per_s": nboot5 / float(t5.item()), "correct": bool(ok5.item())}
-        del a5, b5, c5, out5
+        del a5, b5, c5, out5, a5p, b5p, c5p, out5p
         # c3 / c4 on every rank (weak: per-GPU workloads), reported as the sum over ranks of rank-local rates
         c3 = config_c3(T, np, ctx, sk)
         c4 = config_c4(T, np, local)

@@ -528,10 +528,16 @@ struct Fft {
     fwd_pass<0>(x, tw0); fwd_pass<0>(y, tw0);
     if constexpr (G::NPASS > 1) { exchange2<0, 1>(x, y); fwd_pass<1>(x, tw0); fwd_pass<1>(y, tw0); }
     if constexpr (G::NPASS > 2) { exchange2<1, 2>(x, y); fwd_pass<2>(x, tw0); fwd_pass<2>(y, tw0); }
-    if constexpr (G::NPASS > 3) { exchange2<2, 3>(x, y); fwd_pass<3>(x, tw0); fwd_pass<3>(y, tw0); }
+    if constexpr (G::NPASS > 3) {
+      if constexpr (SHFL_LAST) { last_stage_fwd(x); last_stage_fwd(y); }
+      else { exchange2<2, 3>(x, y); fwd_pass<3>(x, tw0); fwd_pass<3>(y, tw0); }
+    }
   }
   __device__ __forceinline__ void inverse2(double2 (&x)[8], double2 (&y)[8], const Tw4& tw0) {
-    if constexpr (G::NPASS > 3) { inv_pass<3>(x, tw0); inv_pass<3>(y, tw0); exchange2<3, 2>(x, y); }
+    if constexpr (G::NPASS > 3) {
+      if constexpr (SHFL_LAST) { last_stage_inv(x); last_stage_inv(y); }
+      else { inv_pass<3>(x, tw0); inv_pass<3>(y, tw0); exchange2<3, 2>(x, y); }
+    }
     if constexpr (G::NPASS > 2) { inv_pass<2>(x, tw0); inv_pass<2>(y, tw0); exchange2<2, 1>(x, y); }
     if constexpr (G::NPASS > 1) { inv_pass<1>(x, tw0); inv_pass<1>(y, tw0); exchange2<1, 0>(x, y); }
     inv_pass<0>(x, tw0); inv_pass<0>(y, tw0);
@@ -853,7 +859,7 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 #ifndef TFHE_BR_L2_PREFETCH
-#define TFHE_BR_L2_PREFETCH 1   // work items request the key rows of the NEXT chunk (and, at kernel start, of the first) into L2
+#define TFHE_BR_L2_PREFETCH 1   // work items request the key rows of the NEXT chunk (and, at kernel start, of the first) into L2 (N <= 1024: +0.13 % at 128-bit; N = 2048: -0.8 %, off there)
 #endif
 
 // acquire / release on the per-gate progress words of the work-item hand-over
@@ -916,7 +922,8 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
     if (off < bytes)
       prefetch_l2_bulk(reinterpret_cast<const char*>(A.bsk + lo * row_stride) + off, (uint32_t)min(per, bytes - off));
   };
-  if (tau == 0 && blockIdx.x < PF_SLICES) prefetch_chunk(0, blockIdx.x);
+  constexpr bool PF_ON = LOGN <= 10;
+  if (PF_ON && tau == 0 && blockIdx.x < PF_SLICES) prefetch_chunk(0, blockIdx.x);
 #endif
 
   for (;;) {
@@ -928,7 +935,7 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
     const long long g = (long long)(item - (unsigned long long)chunk * (unsigned long long)A.count);
     const int i0 = chunk * A.chunk_steps, i1 = min(n, i0 + A.chunk_steps);
 #if TFHE_BR_L2_PREFETCH
-    if (tau == 0 && g < PF_SLICES && chunk + 1 < A.nchunks) prefetch_chunk(chunk + 1, (unsigned)g);
+    if (PF_ON && tau == 0 && g < PF_SLICES && chunk + 1 < A.nchunks) prefetch_chunk(chunk + 1, (unsigned)g);
 #endif
     const uint32_t* __restrict__ ct = A.ct_in + g * (n + 1);
     // mod switch (evaluator.go:116,122): a~_i = ((a_i + 2^(30-NBIT)) mod 2^32) >> (31-NBIT)
