@@ -202,8 +202,23 @@ def config_c3(T, np, ctx, sk, instances=1024, bits=8, reps=2):
     for _ in range(reps):
         out = run()
     dt = (time.perf_counter() - t0) / reps
+    # the same with the level loop replayed from a CUDA graph (tfhe_ctx_set_circuit_graph): call 1 was the eager run above,
+    # call 2 records, calls 3.. replay
+    graph = {}
+    try:
+        ctx.set_circuit_graph(True)
+        run(); run()
+        r0 = ctx.circuit_graph_replays
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out_g = run()
+        dt_g = (time.perf_counter() - t0) / reps
+        graph = {"bootstraps_per_s_cuda_graph": instances * circ.n_bootstraps / dt_g, "cuda_graph_replays": ctx.circuit_graph_replays - r0,
+                 "cuda_graph_same_words": bool(np.array_equal(out_g, out))}
+    finally:
+        ctx.set_circuit_graph(False)
     s = sum(T.tlwe.DecryptBool(out[i], sk).astype(np.int64) << i for i in range(bits))
-    return {"workload": "%d-bit ripple-carry adder (%d bootstraps, %d levels) x %d instances, tfhe_circuit_run, host buffers"
+    return {**graph, "workload": "%d-bit ripple-carry adder (%d bootstraps, %d levels) x %d instances, tfhe_circuit_run, host buffers"
                         % (bits, circ.n_bootstraps, circ.n_levels, instances),
             "bootstraps_per_s": instances * circ.n_bootstraps / dt, "adders_per_s": instances / dt, "seconds": dt,
             "correct": bool(np.array_equal(s, (x + y) % (1 << bits)))}

@@ -24,7 +24,7 @@ class TfheParams(ctypes.Structure):
 
 ENGINE_SYMBOLS = [
     "tfhe_ctx_create", "tfhe_ctx_create_multi", "tfhe_ctx_device_count", "tfhe_ctx_set_pipeline_chunk", "tfhe_ctx_destroy", "tfhe_last_error", "tfhe_ctx_load_cloudkey",
-    "tfhe_ctx_load_cloudkey_device", "tfhe_bootstrap_batch", "tfhe_bootstrap_batch_indexed", "tfhe_bootstrap_multi_lut_batch", "tfhe_ctx_load_reencryption_key", "tfhe_reencrypt_batch", "tfhe_ctx_set_mux_mode", "tfhe_gate_batch", "tfhe_blind_rotate_batch",
+    "tfhe_ctx_load_cloudkey_device", "tfhe_bootstrap_batch", "tfhe_bootstrap_batch_indexed", "tfhe_bootstrap_multi_lut_batch", "tfhe_ctx_load_reencryption_key", "tfhe_reencrypt_batch", "tfhe_ctx_set_mux_mode", "tfhe_ctx_set_circuit_graph", "tfhe_ctx_circuit_graph_replays", "tfhe_gate_batch", "tfhe_blind_rotate_batch",
     "tfhe_cmux_batch", "tfhe_sample_extract_batch", "tfhe_key_switch_batch", "tfhe_bootstrap_batch_device",
     "tfhe_gate_batch_device", "tfhe_circuit_run", "tfhe_to_fourier_batch", "tfhe_to_poly_batch", "tfhe_mul_poly_batch", "tfhe_ctx_kernel_launches", "tfhe_ctx_set_timing", "tfhe_ctx_set_blind_rotate_variant", "tfhe_ctx_set_blind_rotate_chunk_steps", "tfhe_ctx_set_key_switch_variant", "tfhe_ctx_generate_cloudkey", "tfhe_ctx_collect_timing", "tfhe_ctx_algorithmic_bytes_per_bootstrap", "tfhe_fp64_peak_probe", "tfhe_version",
 ]
@@ -65,6 +65,10 @@ def engine():
             lib.tfhe_ctx_load_reencryption_key.argtypes = [vp, vp, i32, i32]
             lib.tfhe_reencrypt_batch.argtypes = [vp, i64, vp, vp]
             lib.tfhe_ctx_set_mux_mode.argtypes = [vp, ctypes.c_int]
+        if hasattr(lib, "tfhe_ctx_set_circuit_graph"):
+            lib.tfhe_ctx_set_circuit_graph.argtypes = [vp, ctypes.c_int]
+            lib.tfhe_ctx_circuit_graph_replays.argtypes = [vp]
+            lib.tfhe_ctx_circuit_graph_replays.restype = i64
         lib.tfhe_blind_rotate_batch.argtypes = [vp, i64, vp, vp, i64, vp]
         lib.tfhe_cmux_batch.argtypes = [vp, i64, i32, vp, vp, vp]
         lib.tfhe_sample_extract_batch.argtypes = [vp, i64, vp, vp]

@@ -15,6 +15,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <atomic>
 #include <vector>
 
 // TFHE_EXPERIMENTAL: also builds the measured-slower blind-rotate variants of round 1 (TMA-staged / texture key fetch,
@@ -45,11 +46,15 @@ namespace {
 std::string g_create_error;
 std::mutex g_create_mu;
 
+// bumped whenever a device buffer moves: captured CUDA graphs hold raw pointers and are re-captured after any move
+static std::atomic<uint64_t> g_alloc_generation{1};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   cudaError_t reserve(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
+    g_alloc_generation.fetch_add(1, std::memory_order_relaxed);
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
@@ -59,7 +64,7 @@ struct DevBuf {
     if (e == cudaSuccess) cap = want;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  void release() { if (p) { cudaFree(p); g_alloc_generation.fetch_add(1, std::memory_order_relaxed); } p = nullptr; cap = 0; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -108,6 +113,19 @@ struct tfhe_ctx {
   int64_t pipe_chunk = 16384;     // ciphertexts per pipeline chunk
   DevBuf prep, lwe1, tmp, prep2, idx_a, idx_b, ops_dev;       // engine scratch
   DevBuf wires, gate_descs;                                   // circuit runner
+  // circuit runner, CUDA-graph replay (tfhe_ctx_set_circuit_graph): the level loop of a circuit that was already run once
+  // with the same shape is captured on the next call and replayed afterwards
+  struct CircuitGraph {
+    std::vector<tfhe_gate_desc> gates;
+    int32_t n_inputs = 0;
+    int64_t instances = 0;
+    uint64_t gen = 0;            // g_alloc_generation at capture time (0: seen once, not captured yet)
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  };
+  std::vector<CircuitGraph> circuit_graphs;
+  int circuit_graph = 0;          // 0 = off (default), 1 = capture and replay
+  int64_t circuit_graph_replays = 0;
   DevBuf h2d_a, h2d_b, h2d_c, h2d_luts, d2h_out;              // staging for the host-buffer API
   int64_t launches = 0;
   int sm_count = 0;
@@ -883,6 +901,9 @@ void tfhe_ctx_destroy(tfhe_ctx* c) {
   for (DevBuf* b : {&c->wires, &c->gate_descs, &c->prep, &c->lwe1, &c->tmp, &c->prep2, &c->idx_a, &c->idx_b, &c->ops_dev, &c->h2d_a, &c->h2d_b,
                     &c->h2d_c, &c->h2d_luts, &c->d2h_out, &c->br_ctl, &c->br_scratch})
     b->release();
+  for (auto& q : c->circuit_graphs)
+    if (q.exec) cudaGraphExecDestroy(q.exec);
+  c->circuit_graphs.clear();
   for (auto* v : {&c->ev_live, &c->ev_free})
     for (auto& ev : *v) { cudaEventDestroy(ev.e0); cudaEventDestroy(ev.e1); cudaEventDestroy(ev.e2); }
   if (c->bsk_tex) cudaDestroyTextureObject(c->bsk_tex);
@@ -1667,19 +1688,73 @@ int tfhe_circuit_run(tfhe_ctx* c, int64_t instances, int32_t n_inputs, int32_t n
     CK(c, cudaGetLastError());
     return 0;
   };
-  if ((rc = run_linear(0))) return rc;
-  for (int d = 1; d <= max_depth; d++) {
-    const int ng = level_off[d + 1] - level_off[d];
-    if (ng > 0) {
-      const GateDesc* dg = c->gate_descs.as<GateDesc>() + level_off[d];
-      const int64_t jobs = (int64_t)ng * instances;
-      circuit_prepare_kernel<<<(unsigned)jobs, 256, 0, s>>>(dg, instances, c->wires.as<uint32_t>(), c->prep.as<uint32_t>(), c->P.n);
-      c->launches++;
-      CK(c, cudaGetLastError());
-      if ((rc = bootstrap_device(c, jobs, c->prep.as<uint32_t>(), nullptr, 0, c->wires.as<uint32_t>(), s, dg, instances))) return rc;
+  auto run_levels = [&]() -> int {
+    int r = run_linear(0);
+    if (r) return r;
+    for (int d = 1; d <= max_depth; d++) {
+      const int ng = level_off[d + 1] - level_off[d];
+      if (ng > 0) {
+        const GateDesc* dg = c->gate_descs.as<GateDesc>() + level_off[d];
+        const int64_t jobs = (int64_t)ng * instances;
+        circuit_prepare_kernel<<<(unsigned)jobs, 256, 0, s>>>(dg, instances, c->wires.as<uint32_t>(), c->prep.as<uint32_t>(), c->P.n);
+        c->launches++;
+        CK(c, cudaGetLastError());
+        if ((r = bootstrap_device(c, jobs, c->prep.as<uint32_t>(), nullptr, 0, c->wires.as<uint32_t>(), s, dg, instances))) return r;
+      }
+      if ((r = run_linear(d))) return r;
     }
-    if ((rc = run_linear(d))) return rc;
+    return 0;
+  };
+  // CUDA-graph replay of the level loop.  First call with a given (gate list, inputs, instances): eager, which also sizes
+  // every scratch buffer.  Second call: the same launches are captured into a graph (and run).  From then on the graph is
+  // replayed — one launch for the whole circuit — as long as no device buffer has moved since the capture.
+  bool done = false;
+  if (c->circuit_graph && !c->timing) {
+    tfhe_ctx::CircuitGraph* e = nullptr;
+    for (auto& q : c->circuit_graphs)
+      if (q.instances == instances && q.n_inputs == n_inputs && q.gates.size() == (size_t)n_gates &&
+          (n_gates == 0 || !memcmp(q.gates.data(), gates, (size_t)n_gates * sizeof(tfhe_gate_desc)))) { e = &q; break; }
+    const uint64_t gen = g_alloc_generation.load(std::memory_order_relaxed);
+    if (e && e->exec && e->gen == gen) {
+      CK(c, cudaGraphLaunch(e->exec, s));
+      c->launches += e->launches;
+      c->circuit_graph_replays++;
+      done = true;
+    } else if (e) {  // seen before (buffers are sized), or captured before a buffer moved: capture now
+      if (e->exec) { cudaGraphExecDestroy(e->exec); e->exec = nullptr; }
+      const int64_t l0 = c->launches;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int r = run_levels();
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        const bool moved = g_alloc_generation.load(std::memory_order_relaxed) != gen;
+        if (r == 0 && ce == cudaSuccess && graph && !moved && cudaGraphInstantiate(&e->exec, graph, 0) == cudaSuccess) {
+          e->gen = gen;
+          e->launches = c->launches - l0;
+          CK(c, cudaGraphLaunch(e->exec, s));
+          done = true;
+        } else {
+          e->exec = nullptr;
+          cudaGetLastError();    // a capture that could not be completed is not an error of the call: run eagerly below
+          c->launches = l0;
+        }
+        if (graph) cudaGraphDestroy(graph);
+      } else {
+        cudaGetLastError();
+      }
+    } else {
+      if (c->circuit_graphs.size() >= 8) {  // small cache, oldest entry out
+        if (c->circuit_graphs.front().exec) cudaGraphExecDestroy(c->circuit_graphs.front().exec);
+        c->circuit_graphs.erase(c->circuit_graphs.begin());
+      }
+      tfhe_ctx::CircuitGraph q;
+      q.gates.assign(gates, gates + n_gates);
+      q.n_inputs = n_inputs;
+      q.instances = instances;
+      c->circuit_graphs.push_back(std::move(q));
+    }
   }
+  if (!done && (rc = run_levels())) return rc;
   for (int k = 0; k < n_outputs; k++)
     CK(c, cudaMemcpyAsync(outputs + (size_t)k * instances * n1, c->wires.as<char>() + (size_t)output_wires[k] * wire_bytes, wire_bytes,
                           cudaMemcpyDeviceToHost, s));
@@ -1788,6 +1863,25 @@ int tfhe_ctx_set_mux_mode(tfhe_ctx* c, int mode) {
   if (!c || mode < 0 || mode > 1) return fail(c, TFHE_ERR_ARG, "mux mode must be 0 (three bootstraps) or 1 (two blind rotations + one key switch)");
   c->mux_mode = mode;
   return TFHE_OK;
+}
+
+// tfhe_circuit_run: 1 = capture the level loop of a repeated circuit into a CUDA graph and replay it (results identical).
+int tfhe_ctx_set_circuit_graph(tfhe_ctx* c, int enable) {
+  GROUP_FORWARD(c, tfhe_ctx_set_circuit_graph(kid, enable));
+  if (!c) return TFHE_ERR_ARG;
+  c->circuit_graph = enable ? 1 : 0;
+  if (!enable) {
+    for (auto& q : c->circuit_graphs)
+      if (q.exec) cudaGraphExecDestroy(q.exec);
+    c->circuit_graphs.clear();
+  }
+  return TFHE_OK;
+}
+int64_t tfhe_ctx_circuit_graph_replays(const tfhe_ctx* c) {
+  if (!c) return 0;
+  int64_t total = c->circuit_graph_replays;
+  for (const tfhe_ctx* k : c->kids) total += k->circuit_graph_replays;
+  return total;
 }
 
 // CMUX steps per work item of the persistent throughput kernel: 0 = automatic, >= n = whole gates per item.

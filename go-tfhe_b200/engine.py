@@ -167,6 +167,14 @@ class Context:
         self._ck(self.lib.tfhe_reencrypt_batch(self.h, len(ct), _ptr(ct), _ptr(out)), "tfhe_reencrypt_batch")
         return out
 
+    def set_circuit_graph(self, enable=True):
+        """CUDA-graph replay of repeated circuits in circuit_run (off by default; results identical)."""
+        self._ck(self.lib.tfhe_ctx_set_circuit_graph(self.h, 1 if enable else 0), "tfhe_ctx_set_circuit_graph")
+
+    @property
+    def circuit_graph_replays(self):
+        return int(self.lib.tfhe_ctx_circuit_graph_replays(self.h))
+
     def set_mux_mode(self, mode):
         """0 = the reference's three-bootstrap MUX (default), 1 = two blind rotations + one key switch (opt-in)."""
         self._ck(self.lib.tfhe_ctx_set_mux_mode(self.h, int(mode)), "tfhe_ctx_set_mux_mode")

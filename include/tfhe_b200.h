@@ -225,6 +225,13 @@ int tfhe_ctx_set_blind_rotate_variant(tfhe_ctx* ctx, int variant);
  * without key switch (gates.bootstrapWithoutKeySwitch, gates.go:145-149), summed with 1/8 and key-switched once: two blind
  * rotations instead of three; same truth table, but NOT the reference's ciphertext words (hence opt-in). */
 int tfhe_ctx_set_mux_mode(tfhe_ctx* ctx, int mode);
+/* tfhe_circuit_run, CUDA-graph replay (off by default).  When enabled, the first call with a given (gate list, n_inputs,
+ * instances) runs as usual — which also sizes every scratch buffer —, the second call records the same per-level
+ * launches into a CUDA graph, and later calls replay that graph with one launch, for as long as no device buffer of the
+ * library has been reallocated since (otherwise it is recorded again).  Results are identical; what it removes is the
+ * per-launch host cost (~100 launches for an 8-bit adder).  tfhe_ctx_circuit_graph_replays counts the replays. */
+int tfhe_ctx_set_circuit_graph(tfhe_ctx* ctx, int enable);
+int64_t tfhe_ctx_circuit_graph_replays(const tfhe_ctx* ctx);
 /* The throughput kernel runs persistent blocks over WORK ITEMS of `steps` consecutive CMUX steps of one gate (the
  * accumulator is handed from item to item through device memory), so that a batch that is not a multiple of the
  * resident blocks still fills the SMs to the end.  0 = automatic (default: whole gates for batches that fit the

@@ -207,3 +207,47 @@ def test_c5_mixed_gates_sharded_by_index_reduced(T, O, keyset):
     finally:
         ctx.close()
         multi.close()
+
+
+def test_circuit_graph_replay_is_identical(T, O, env):
+    """tfhe_ctx_set_circuit_graph: call 1 of a circuit shape runs eagerly, call 2 records the level loop into a CUDA graph,
+    calls 3+ replay it.  Every call must give the words of the plain runner on its own inputs; another shape gets its own
+    graph; a reallocation of any device buffer in between forces a re-capture and still gives the same words."""
+    P, sk, ck, _ = env
+    ctx = T.Context(T.params.get("80"), 0)           # a fresh context: its scratch buffers start small
+    ctx.load_cloudkey(ck.offset, ck.bsk_fft, ck.ksk, ck.testvec)
+    circ = T.circuit.ripple_carry_adder(3)
+    n_in = 7
+
+    def wires(inst, seed):
+        rng = np.random.default_rng(seed)
+        x, y = rng.integers(0, 8, inst), rng.integers(0, 8, inst)
+        ins = np.stack([sk.encrypt_bool((x >> i) & 1, seed + i) for i in range(3)] + [sk.encrypt_bool((y >> i) & 1, seed + 10 + i) for i in range(3)])
+        return np.concatenate([ins, np.broadcast_to(O.constant(P, False), (1, inst, P.n + 1))]), (x + y) % 8
+
+    plain = {}
+    for inst, seed in ((9, 1), (9, 2), (9, 3), (9, 4), (5, 5), (5, 6), (5, 7)):
+        w, _ = wires(inst, seed)
+        plain[(inst, seed)] = ctx.circuit_run(circ.gates, n_in, w, circ.out_wires)
+    try:
+        ctx.set_circuit_graph(True)
+        r0 = ctx.circuit_graph_replays
+        for inst, seed in ((9, 1), (9, 2), (9, 3), (5, 5), (5, 6), (5, 7), (9, 4)):
+            w, want = wires(inst, seed)
+            got = ctx.circuit_run(circ.gates, n_in, w, circ.out_wires)
+            assert np.array_equal(got, plain[(inst, seed)]), (inst, seed)
+            s = sum(sk.decrypt_bool(got[i]).astype(np.int64) << i for i in range(3))
+            assert np.array_equal(s, want)
+        assert ctx.circuit_graph_replays - r0 == 3          # (9,3), (5,7), (9,4): third and later calls of a shape
+        # a much larger batch grows the engine's scratch buffers: the recorded graphs hold stale pointers and must not be used
+        big = sk.encrypt_bool(np.arange(3000) % 2, 77)
+        ctx.gate_batch("NAND", big, big)
+        r1 = ctx.circuit_graph_replays
+        w, _ = wires(9, 2)
+        assert np.array_equal(ctx.circuit_run(circ.gates, n_in, w, circ.out_wires), plain[(9, 2)])   # re-captured
+        assert ctx.circuit_graph_replays == r1
+        assert np.array_equal(ctx.circuit_run(circ.gates, n_in, w, circ.out_wires), plain[(9, 2)])   # replayed
+        assert ctx.circuit_graph_replays == r1 + 1
+    finally:
+        ctx.set_circuit_graph(False)
+        ctx.close()
