@@ -380,3 +380,146 @@ func (e *Engine) BlindRotateBatch(cts []*tlwe.TLWELv0, luts []*trlwe.TRLWELv1) [
 	}
 	return res
 }
+
+// ---- additive entry points (no counterpart in the reference; SURVEY 8(b) "additive", 8(f) ranks 1 and 4) --------------
+
+// Gate is one gate of a circuit over wire ids (tfhe_gate_desc): wires 0..nInputs-1 are the inputs, every gate writes a
+// distinct wire >= nInputs and reads only inputs or wires written by earlier gates.  In2 is read by MUX only.
+type Gate struct {
+	Op                 Op
+	In0, In1, In2, Out int
+}
+
+// CircuitRun evaluates the same circuit on len(inputs[w]) independent instances (tfhe_circuit_run): one batch per
+// level, intermediate wires resident on the GPUs, whole instances per device.  inputs[w][k] is input wire w of instance
+// k; the result is indexed [output][instance].  Every gate computes exactly what gates.X computes.
+func (e *Engine) CircuitRun(gatesList []Gate, inputs [][]*tlwe.TLWELv0, outputWires []int) [][]*tlwe.TLWELv0 {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	if len(inputs) == 0 || len(outputWires) == 0 {
+		return nil
+	}
+	instances := len(inputs[0])
+	if instances == 0 {
+		return make([][]*tlwe.TLWELv0, len(outputWires))
+	}
+	flat := make([]uint32, 0, len(inputs)*instances*(e.n+1))
+	for _, wire := range inputs {
+		if len(wire) != instances {
+			panic("tfheb200: every input wire needs the same number of instances")
+		}
+		flat = append(flat, e.flatten(wire)...)
+	}
+	descs := make([]C.tfhe_gate_desc, len(gatesList))
+	for i, g := range gatesList {
+		descs[i].op = C.uint8_t(g.Op)
+		descs[i].in0, descs[i].in1, descs[i].in2, descs[i].out = C.int32_t(g.In0), C.int32_t(g.In1), C.int32_t(g.In2), C.int32_t(g.Out)
+	}
+	ow := make([]C.int32_t, len(outputWires))
+	for i, w := range outputWires {
+		ow[i] = C.int32_t(w)
+	}
+	out := make([]uint32, len(outputWires)*instances*(e.n+1))
+	var pd *C.tfhe_gate_desc
+	if len(descs) > 0 {
+		pd = &descs[0]
+	}
+	e.check(C.tfhe_circuit_run(e.ctx, C.int64_t(instances), C.int32_t(len(inputs)), C.int32_t(len(descs)), pd,
+		(*C.uint32_t)(&flat[0]), C.int32_t(len(ow)), &ow[0], (*C.uint32_t)(&out[0])), "tfhe_circuit_run")
+	runtime.KeepAlive(descs)
+	res := make([][]*tlwe.TLWELv0, len(outputWires))
+	per := instances * (e.n + 1)
+	for k := range res {
+		res[k] = e.unflatten(out[k*per:(k+1)*per], instances)
+	}
+	return res
+}
+
+// SetCircuitGraph turns the CUDA-graph replay of repeated circuits on or off (tfhe_ctx_set_circuit_graph).
+func (e *Engine) SetCircuitGraph(on bool) {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	v := C.int(0)
+	if on {
+		v = 1
+	}
+	e.check(C.tfhe_ctx_set_circuit_graph(e.ctx, v), "tfhe_ctx_set_circuit_graph")
+}
+
+// SetMuxMode: 0 = gates.MUX exactly (three bootstraps), 1 = two blind rotations + one key switch (tfhe_ctx_set_mux_mode).
+func (e *Engine) SetMuxMode(mode int) {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	e.check(C.tfhe_ctx_set_mux_mode(e.ctx, C.int(mode)), "tfhe_ctx_set_mux_mode")
+}
+
+func flattenLUTs(luts []*trlwe.TRLWELv1) []uint32 {
+	var fl []uint32
+	for _, l := range luts {
+		fl = appendTorus(appendTorus(fl, l.A), l.B)
+	}
+	return fl
+}
+
+// BootstrapBatchIndexed is BootstrapLUTAssign for a batch that draws its LUTs from a small table: ciphertext k uses
+// luts[index[k]] (tfhe_bootstrap_batch_indexed) — the table crosses the bus once instead of one 8-16 KiB LUT per ciphertext.
+func (e *Engine) BootstrapBatchIndexed(cts []*tlwe.TLWELv0, luts []*trlwe.TRLWELv1, index []int32) []*tlwe.TLWELv0 {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	count := len(cts)
+	if count == 0 {
+		return nil
+	}
+	if len(index) != count || len(luts) == 0 {
+		panic("tfheb200: BootstrapBatchIndexed needs one index per ciphertext and a non-empty LUT table")
+	}
+	in, out, fl := e.flatten(cts), make([]uint32, count*(e.n+1)), flattenLUTs(luts)
+	e.check(C.tfhe_bootstrap_batch_indexed(e.ctx, C.int64_t(count), (*C.uint32_t)(&in[0]), (*C.uint32_t)(&fl[0]),
+		C.int64_t(len(luts)), (*C.int32_t)(&index[0]), (*C.uint32_t)(&out[0])), "tfhe_bootstrap_batch_indexed")
+	return e.unflatten(out, count)
+}
+
+// BootstrapMultiLUT evaluates 2^log2K functions of every ciphertext with ONE blind rotation each
+// (tfhe_bootstrap_multi_lut_batch); packed holds one packed test vector per ciphertext or a single one for all.  The
+// result is indexed [ciphertext][function].
+func (e *Engine) BootstrapMultiLUT(cts []*tlwe.TLWELv0, packed []*trlwe.TRLWELv1, log2K int) [][]*tlwe.TLWELv0 {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	count := len(cts)
+	if count == 0 {
+		return nil
+	}
+	k := 1 << log2K
+	in, out, fl := e.flatten(cts), make([]uint32, count*k*(e.n+1)), flattenLUTs(packed)
+	e.check(C.tfhe_bootstrap_multi_lut_batch(e.ctx, C.int64_t(count), (*C.uint32_t)(&in[0]), (*C.uint32_t)(&fl[0]),
+		C.int64_t(len(packed)), C.int32_t(log2K), (*C.uint32_t)(&out[0])), "tfhe_bootstrap_multi_lut_batch")
+	res := make([][]*tlwe.TLWELv0, count)
+	per := k * (e.n + 1)
+	for i := range res {
+		res[i] = e.unflatten(out[i*per:(i+1)*per], k)
+	}
+	return res
+}
+
+// LoadReencryptionKey uploads proxyreenc.ProxyReencryptionKey.KeyEncryptions (proxyreenc/proxyreenc.go:249-300: row
+// base*t*i + base*j + k, each a TLWELv0 under the target key) with its Base = 2^basebit and T.
+func (e *Engine) LoadReencryptionKey(rows []*tlwe.TLWELv0, basebit, t int) {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	flat := e.flatten(rows)
+	e.check(C.tfhe_ctx_load_reencryption_key(e.ctx, (*C.uint32_t)(&flat[0]), C.int32_t(basebit), C.int32_t(t)),
+		"tfhe_ctx_load_reencryption_key")
+}
+
+// ReencryptBatch replaces proxyreenc.ReencryptTLWELv0 (proxyreenc/proxyreenc.go:321-366) applied element-wise.
+func (e *Engine) ReencryptBatch(cts []*tlwe.TLWELv0) []*tlwe.TLWELv0 {
+	e.mu.Lock()
+	defer e.mu.Unlock()
+	count := len(cts)
+	if count == 0 {
+		return nil
+	}
+	in, out := e.flatten(cts), make([]uint32, count*(e.n+1))
+	e.check(C.tfhe_reencrypt_batch(e.ctx, C.int64_t(count), (*C.uint32_t)(&in[0]), (*C.uint32_t)(&out[0])), "tfhe_reencrypt_batch")
+	return e.unflatten(out, count)
+}
