@@ -886,7 +886,9 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 // ---------------------------------------------------------------------------------------------
 // TFHE_BR_LB_THREADS / TFHE_BR_LB_BLOCKS: experiment knob — declare looser launch bounds than the real block size to
 // steer ptxas to a register budget between the (64,4) -> 255 and (64,5) -> 168 choices, e.g. (160,2) -> ~200.
-#ifdef TFHE_BR_LB_THREADS
+#if defined(TFHE_BR_MAXNREG)   // experiment knob: an explicit register cap for every instance of the throughput kernel
+#define TFHE_BR_BOUNDS(T, MINB) __maxnreg__(TFHE_BR_MAXNREG)
+#elif defined(TFHE_BR_LB_THREADS)
 #define TFHE_BR_BOUNDS(T, MINB) __launch_bounds__(TFHE_BR_LB_THREADS, TFHE_BR_LB_BLOCKS)
 #else
 #define TFHE_BR_BOUNDS(T, MINB) __launch_bounds__(T, MINB)
