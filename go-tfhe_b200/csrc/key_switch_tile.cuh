@@ -6,7 +6,7 @@
 // 52 GB through the L2->SM fabric (3.5 ms, profiles/r02_ks_gather_uint5_ncu_full_metrics.csv).  A dense one-hot
 // contraction on the tensor cores (the basebit = 2 path) would be base-1 = 63 times the work.  Here a block owns a TILE
 // of 256 ciphertexts x 64 output words and walks the (i, j) pairs; for each pair the `base` candidate rows' 64-word
-// column slices (16 KiB at base 64) are staged ONCE in shared memory (one TMA box per pair, 4 stages in flight on mbarriers) and each of the 256
+// column slices are staged ONCE in shared memory (one 32 KiB TMA box of 128 key rows = 128 / base pairs per stage, 3 stages in flight on mbarriers) and each of the 256
 // ciphertexts adds the slice its digit selects: every key byte leaves L2 once per 256 ciphertexts instead of once per
 // ciphertext (13.7 GB instead of 52 GB), the selection itself becomes a shared-memory read.  Sums are u32 and commute:
 // bit-identical to the gather and to the oracle.  K = N*t pairs are split over several blocks per tile (red.global.add
@@ -27,8 +27,9 @@ namespace tfhe {
 constexpr int KST_CT = 256;      // ciphertexts per tile
 constexpr int KST_COLS = 64;     // output words per tile (16 uint4)
 constexpr int KST_THREADS = 512; // 16 column quads x 32 ciphertext groups of 8
-constexpr int KST_STAGES = 4;   // power of two
-__host__ __device__ constexpr size_t kst_smem_bytes(int base) { return (size_t)KST_STAGES * base * KST_COLS * 4; }
+constexpr int KST_STAGES = 3;
+constexpr int KST_STAGE_ROWS = 128;  // key rows per stage = 128 / base (i, j) pairs: 32 KiB, one TMA box
+__host__ __device__ constexpr size_t kst_smem_bytes(int) { return (size_t)KST_STAGES * KST_STAGE_ROWS * KST_COLS * 4; }
 
 // lwe_in [count][N+1] -> digits D[(i*t+j)][cpad] and out rows initialised to (0,...,0,b).
 // grid (cpad / 256, N / 8), 256 threads: thread = ciphertext, blockIdx.y = group of 8 mask words (one 32-byte sector).
@@ -66,13 +67,15 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
                                                                  uint32_t* __restrict__ out, int K, long long count, long long cpad,
                                                                  int n, int col_tiles, int ksplit, int ct_tiles,
                                                                  const GateDesc* __restrict__ out_gates, long long instances) {
-  extern __shared__ __align__(128) uint4 slab[];  // [KST_STAGES][BASE][16]
+  extern __shared__ __align__(128) uint4 slab[];  // [KST_STAGES][KST_STAGE_ROWS][16]
   __shared__ __align__(8) uint64_t full_bar[KST_STAGES];
-  constexpr uint32_t STAGE_BYTES = BASE * 16 * 16;
+  constexpr int PP = KST_STAGE_ROWS / BASE;        // (i, j) pairs per stage
+  constexpr uint32_t STAGE_BYTES = KST_STAGE_ROWS * 16 * 16;
   const int tid = threadIdx.x;
   const int ct_tile = blockIdx.x % ct_tiles;
   const int rest = blockIdx.x / ct_tiles;
   const int ks = rest % ksplit, col_tile = rest / ksplit;
+  // K counts stages (groups of PP pairs) here
   const int s_lo = (int)(((long long)K * ks) / ksplit), s_hi = (int)(((long long)K * (ks + 1)) / ksplit);
   const int nst = s_hi - s_lo;
   const int colq = tid & 15, ctg = tid >> 4;
@@ -84,36 +87,40 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
-  // one TMA box per stage: BASE rows x 64 words of the key ([rows][stride] u32), columns past the row end arrive as zeros
+  // one TMA box per stage: 128 rows x 64 words of the key ([rows][stride] u32), columns past the row end arrive as zeros
   auto fill = [&](int s, int buf) {
     mbar_arrive_expect_tx(&full_bar[buf], STAGE_BYTES);
-    tma_load_2d(smem0 + buf * STAGE_BYTES, &key_map, col_tile * KST_COLS, (s_lo + s) * BASE, smem_u32(&full_bar[buf]));
+    tma_load_2d(smem0 + buf * STAGE_BYTES, &key_map, col_tile * KST_COLS, (s_lo + s) * KST_STAGE_ROWS, smem_u32(&full_bar[buf]));
   };
   if (tid == 0)
     for (int p = 0; p < KST_STAGES - 1 && p < nst; p++) fill(p, p);
-  const uint2* dig = reinterpret_cast<const uint2*>(D + (size_t)s_lo * cpad + c0);
+  const uint2* dig = reinterpret_cast<const uint2*>(D + (size_t)s_lo * PP * cpad + c0);
   const size_t dig_step = (size_t)cpad / 8;  // uint2 per pair
   uint4 acc[8];
 #pragma unroll
   for (int u = 0; u < 8; u++) acc[u] = make_uint4(0u, 0u, 0u, 0u);
   uint2 dnext = nst > 0 ? __ldg(dig) : make_uint2(0u, 0u);
   int buf = 0;
+  uint32_t phase = 0;
   for (int s = 0; s < nst; s++) {
     __syncthreads();  // everyone is done reading the buffer refilled below (stage s - 1)
-    if (tid == 0 && s + KST_STAGES - 1 < nst) fill(s + KST_STAGES - 1, (buf + KST_STAGES - 1) & (KST_STAGES - 1));
-    mbar_wait(&full_bar[buf], (uint32_t)(s / KST_STAGES) & 1u);  // stage s has landed
-    const uint2 d = dnext;
-    dig += dig_step;
-    if (s + 1 < nst) dnext = __ldg(dig);
-    const unsigned char* rd = reinterpret_cast<const unsigned char*>(slab) + colq * 16 + buf * STAGE_BYTES;
+    if (tid == 0 && s + KST_STAGES - 1 < nst) fill(s + KST_STAGES - 1, buf == 0 ? KST_STAGES - 1 : buf - 1);
+    mbar_wait(&full_bar[buf], phase);  // stage s has landed
+#pragma unroll 2
+    for (int pp = 0; pp < PP; pp++) {
+      const uint2 d = dnext;
+      dig += dig_step;
+      if (pp + 1 < PP || s + 1 < nst) dnext = __ldg(dig);
+      const unsigned char* rd = reinterpret_cast<const unsigned char*>(slab) + colq * 16 + buf * STAGE_BYTES + pp * (BASE * 256);
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      // byte u of the digit word, times the 256-byte row pitch: one byte permute puts it in bits 8..15
-      const uint32_t off = __byte_perm(u < 4 ? d.x : d.y, 0u, 0x4404u | ((uint32_t)(u & 3) << 4));
-      const uint4 v = *reinterpret_cast<const uint4*>(rd + off);
-      acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+      for (int u = 0; u < 8; u++) {
+        // byte u of the digit word, times the 256-byte row pitch: one byte permute puts it in bits 8..15
+        const uint32_t off = __byte_perm(u < 4 ? d.x : d.y, 0u, 0x4404u | ((uint32_t)(u & 3) << 4));
+        const uint4 v = *reinterpret_cast<const uint4*>(rd + off);
+        acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+      }
     }
-    buf = (buf + 1) & (KST_STAGES - 1);
+    if (++buf == KST_STAGES) { buf = 0; phase ^= 1u; }
   }
   const int cw = col_tile * KST_COLS + colq * 4;
 #pragma unroll

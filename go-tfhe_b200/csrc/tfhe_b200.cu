@@ -570,15 +570,16 @@ int launch_key_switch_tile(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, u
   // split the (i, j) pairs of a tile over `ksplit` blocks so that the blocks fill whole rounds of the resident slots
   // (2 per SM); each block pays ~24 pairs' worth of prologue + epilogue
   const int64_t tiles = ct_tiles * col_tiles, slots = 2 * (int64_t)c->sm_count;
+  const int stages = K / (KST_STAGE_ROWS / base);   // a stage = 128 key rows = 128 / base pairs (N * t is a multiple of 8)
   int best = 1;
   double best_cost = 1e300;
-  for (int ks = 1; ks <= 64 && ks * 64 <= K; ks++) {
+  for (int ks = 1; ks <= 64 && ks * 32 <= stages; ks++) {
     const double rounds = std::ceil((double)tiles * ks / slots);
-    const double cost = rounds * ((double)K / ks + 24.0);
+    const double cost = rounds * ((double)stages / ks + 12.0);
     if (cost < best_cost) { best_cost = cost; best = ks; }
   }
   auto kern = base == 64 ? ks_tile_kernel<64> : base == 32 ? ks_tile_kernel<32> : ks_tile_kernel<16>;
-  kern<<<(unsigned)(tiles * best), KST_THREADS, kst_smem_bytes(base), s>>>(c->ks_tile_map, c->ks_sel.as<uint8_t>(), d_out, K, count, cpad, P.n,
+  kern<<<(unsigned)(tiles * best), KST_THREADS, kst_smem_bytes(base), s>>>(c->ks_tile_map, c->ks_sel.as<uint8_t>(), d_out, stages, count, cpad, P.n,
                                                                        col_tiles, best, (int)ct_tiles, out_gates, instances);
   c->launches++;
   CK(c, cudaGetLastError());
@@ -956,8 +957,8 @@ int tfhe_ctx_load_cloudkey_device(tfhe_ctx* c, uint32_t offset, const double* d_
     CK(c, cudaGetLastError());
     c->has_ksk = true;
     c->ks_tile_ok = false;
-    if (P.basebit >= 4 && P.basebit <= 6 && encode_tiled_fn()) {
-      int rcm = make_u32_map(c, &c->ks_tile_map, c->d_ksk, c->ksk_stride, (long long)rows, KST_COLS, 1 << P.basebit);
+    if (P.basebit >= 4 && P.basebit <= 6 && (P.N * P.iks_t) % (KST_STAGE_ROWS >> P.basebit) == 0 && encode_tiled_fn()) {
+      int rcm = make_u32_map(c, &c->ks_tile_map, c->d_ksk, c->ksk_stride, (long long)rows, KST_COLS, KST_STAGE_ROWS);
       if (rcm) return rcm;
       c->ks_tile_ok = true;
     }
