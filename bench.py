@@ -115,24 +115,28 @@ def profile_traffic():
         return None
 
 
-def cpu_baseline(threads, gates_per_thread=16):
+def cpu_baseline(threads, target_s=12.0):
     """Oracle (port of the reference's Go path) on the host cores: one worker thread per core, private scratch —
-    the trgsw.BatchBlindRotate goroutine-per-gate equivalent.  Returns gates/s on a bounded sample."""
+    the trgsw.BatchBlindRotate goroutine-per-gate equivalent.  Returns gates/s on a bounded sample: a short probe (one
+    gate per thread) sizes the sample to ~target_s seconds of work, capped at the workload's 4096 gates."""
     from oracle import oracle as O
     P = O.get_params(PARAMS)
     sk = O.SecretKey(P, 11)
     ck = O.CloudKey(sk, 12, threads=threads)
-    count = threads * gates_per_thread
     import numpy as np
     rng = np.random.default_rng(5)
-    A = rng.integers(0, 2, count).astype(np.uint8)
-    B = rng.integers(0, 2, count).astype(np.uint8)
+    A = rng.integers(0, 2, 4096).astype(np.uint8)
+    B = rng.integers(0, 2, 4096).astype(np.uint8)
     a, b = sk.encrypt_bool(A, 1), sk.encrypt_bool(B, 2)
     O.gate_batch(ck, OP, a[:threads], b[:threads], threads=threads)  # warm
     t0 = time.perf_counter()
-    out = O.gate_batch(ck, OP, a, b, threads=threads)
+    O.gate_batch(ck, OP, a[:threads], b[:threads], threads=threads)
+    per_round = max(time.perf_counter() - t0, 1e-3)
+    count = int(min(4096, max(1, round(target_s / per_round)) * threads))
+    t0 = time.perf_counter()
+    out = O.gate_batch(ck, OP, a[:count], b[:count], threads=threads)
     dt = time.perf_counter() - t0
-    assert np.array_equal(sk.decrypt_bool(out), 1 - (A & B))
+    assert np.array_equal(sk.decrypt_bool(out), 1 - (A[:count] & B[:count]))
     return count / dt, count, dt
 
 
@@ -579,7 +583,7 @@ def main():
             threads = os.cpu_count() or 1
             v, cnt, dt = cpu_baseline(threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "%d NAND gates (16 per host thread), 128-bit, %.1f s; oracle = C++ port of the "
+                                    "sample": "%d NAND gates of the 4096-gate workload, 128-bit, %.1f s; oracle = C++ port of the "
                                               "reference's Go path (no Go toolchain in this image)" % (cnt, dt)}
         print(json.dumps(line), flush=True)
     ctx.close()
