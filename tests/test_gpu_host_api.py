@@ -251,3 +251,27 @@ def test_circuit_graph_replay_is_identical(T, O, env):
     finally:
         ctx.set_circuit_graph(False)
         ctx.close()
+
+
+def test_circuit_levels_through_the_tiled_key_switch(T, O, keyset):
+    """A circuit on a large-base parameter set (Uint3: base 64) with enough instances that every level's key switch takes the
+    shared-memory tile kernel, whose blocks then scatter to WIRE rows (job -> (gate of the level, instance) -> wire):
+    the words must equal those of the same run with the row gather."""
+    P, sk, ck = keyset("uint3")
+    ctx = T.Context(T.params.get("uint3"), 0)
+    try:
+        ctx.load_cloudkey(ck.offset, ck.bsk_fft, ck.ksk, ck.testvec)
+        circ = T.circuit.ripple_carry_adder(2)
+        inst = 170
+        rng = np.random.default_rng(3)
+        ins = np.stack([sk.encrypt_bool(rng.integers(0, 2, inst).astype(np.uint8), 40 + i) for i in range(4)])
+        wires = np.concatenate([ins, np.broadcast_to(O.constant(P, False), (1, inst, P.n + 1))])
+        ctx.set_key_switch_variant("gather")
+        ref = ctx.circuit_run(circ.gates, 5, wires, circ.out_wires)
+        ctx.set_key_switch_variant("tile")
+        got = ctx.circuit_run(circ.gates, 5, wires, circ.out_wires)
+        ctx.set_key_switch_variant("auto")
+        assert np.array_equal(got, ref)
+        assert np.array_equal(ctx.circuit_run(circ.gates, 5, wires, circ.out_wires), ref)
+    finally:
+        ctx.close()
