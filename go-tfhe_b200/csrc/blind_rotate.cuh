@@ -78,6 +78,7 @@ struct Tw4 { double2 s[4]; };  // twiddles of one radix-8 block: S(m,i), S(2m,2i
 __constant__ Tw4 c_tw_pass1[3][8];  // [LOGM - 8][block] : pass-1 twiddles of the M = 256, 512, 1024 transforms
 #endif
 
+constexpr int BR_MAX_TAIL = 7;
 struct BrArgs {
   const uint32_t* ct_in;    // [count][n+1]  (already linearly combined)
   const uint32_t* testvec;  // [2][N] default test vector
@@ -97,11 +98,20 @@ struct BrArgs {
   // work distribution of the persistent throughput kernel (blind_rotate_kernel); ignored by the latency kernels
   long long count;          // gates in this launch
   int nchunks;              // work items per gate (1 = a whole gate per item)
-  int chunk_steps;          // CMUX steps per work item, nchunks * chunk_steps >= n
+  int chunk_steps;          // CMUX steps per work item of the first main_chunks items
+  int main_chunks;          // items of chunk_steps steps; the remaining nchunks - main_chunks items are the graded tail:
+  int tail_start[BR_MAX_TAIL + 1];  // item main_chunks + k covers steps [tail_start[k], tail_start[k + 1]) — ever shorter
+                            // items at the end of every gate, so that the blocks of a launch finish close together
   uint32_t* scratch;        // [count][2][N] accumulator hand-over between the items of a gate (nchunks > 1)
   unsigned int* ctl;        // [0] next work item, [1] finished blocks; zero at launch, re-zeroed by the last block
   int* progress;            // [count] items finished per gate (nchunks > 1); zero at launch, re-zeroed by the last block
 };
+
+// first CMUX step of work item `ch` of a gate (ch == nchunks: n)
+__device__ __forceinline__ int br_chunk_lo(const BrArgs& A, int ch) {
+  if (ch < A.main_chunks) return ch * A.chunk_steps;
+  return ch >= A.nchunks ? A.n : A.tail_start[ch - A.main_chunks];
+}
 
 struct CmuxArgs {
   const uint32_t* ct0;      // NULL => zero (plain external product)
@@ -917,7 +927,7 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
   // time, in slices, by the bulk-copy unit: chunk 0 by all blocks at entry, chunk c + 1 by the first items of chunk c.
   constexpr int PF_SLICES = 256;
   auto prefetch_chunk = [&](int ch, unsigned slice) {
-    const size_t lo = (size_t)ch * A.chunk_steps, hi = (size_t)min(n, (ch + 1) * A.chunk_steps);
+    const size_t lo = (size_t)br_chunk_lo(A, ch), hi = (size_t)br_chunk_lo(A, ch + 1);
     if (lo >= hi) return;
     const size_t bytes = (hi - lo) * row_stride * sizeof(double2), per = (bytes / PF_SLICES + 15) / 16 * 16;
     const size_t off = (size_t)slice * per;
@@ -935,7 +945,7 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
     if (item >= total) break;
     const int chunk = (int)(item / (unsigned long long)A.count);
     const long long g = (long long)(item - (unsigned long long)chunk * (unsigned long long)A.count);
-    const int i0 = chunk * A.chunk_steps, i1 = min(n, i0 + A.chunk_steps);
+    const int i0 = br_chunk_lo(A, chunk), i1 = br_chunk_lo(A, chunk + 1);
 #if TFHE_BR_L2_PREFETCH
     if (PF_ON && tau == 0 && g < PF_SLICES && chunk + 1 < A.nchunks) prefetch_chunk(chunk + 1, (unsigned)g);
 #endif

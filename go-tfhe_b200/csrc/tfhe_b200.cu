@@ -101,6 +101,7 @@ struct tfhe_ctx {
   CUtensorMap ks_tile_map{};      // the repacked key-switching key as [rows][stride] u32, box = base rows x 64 words (key_switch_tile.cuh)
   bool ks_tile_ok = false;
   int ks_variant = 0;              // 0 = auto, 1 = row gather (key_switch_kernel), 2 = tensor-core contraction, 3 = shared-memory tiles (ks_tile_kernel)
+  int br_tail_min = 6;            // shortest piece of the graded tail of a gate's work items (steps); >= n: no grading
   int mux_mode = 0;                // 0 = the reference's three bootstraps per MUX, 1 = two blind rotations + one key switch
   // proxy re-encryption key (proxyreenc.ProxyReencryptionKey.KeyEncryptions): [n*t*base][stride] rows under the target key
   uint32_t* d_reenc = nullptr;
@@ -354,24 +355,41 @@ int set_device(tfhe_ctx* c) {
 // balance).  Larger batches are cut into items of ~n/14 steps, the count in [10, 20] chosen so that the LAST round of
 // items over the resident blocks is as full as possible (4096 gates at n = 700 over 592 blocks: 13 items of 54 steps =
 // 89.95 rounds).
-void pick_chunks(const tfhe_ctx* c, int64_t count, int* nchunks, int* chunk_steps) {
+void pick_chunks(const tfhe_ctx* c, int64_t count, BrArgs* a) {
   const int n = c->P.n;
   const int64_t resident = (int64_t)c->sm_count * c->br_blocks_per_sm;
-  *nchunks = 1; *chunk_steps = n;
-  if (c->br_chunk_steps > 0) {
-    *chunk_steps = std::min(n, c->br_chunk_steps);
-    *nchunks = (n + *chunk_steps - 1) / *chunk_steps;
+  a->nchunks = 1; a->chunk_steps = n; a->main_chunks = 1;
+  for (int k = 0; k <= BR_MAX_TAIL; k++) a->tail_start[k] = n;
+  if (c->br_chunk_steps > 0) {  // forced: uniform items
+    a->chunk_steps = std::min(n, c->br_chunk_steps);
+    a->nchunks = a->main_chunks = (n + a->chunk_steps - 1) / a->chunk_steps;
     return;
   }
   if (count <= resident || n < 64) return;
   double best = 1e300;
+  int kk_best = 1, steps_best = n;
   for (int k = 10; k <= 20; k++) {
     const int steps = (n + k - 1) / k;
     const int kk = (n + steps - 1) / steps;
     const double rounds = (double)count * kk / (double)resident;
     const double cost = std::ceil(rounds) / rounds * (1.0 + 0.0005 * kk);  // last-round fill, small per-item overhead
-    if (cost < best) { best = cost; *nchunks = kk; *chunk_steps = steps; }
+    if (cost < best) { best = cost; kk_best = kk; steps_best = steps; }
   }
+  // Graded tail: the blocks of a launch finish spread over one item's duration (half of it idle on average, ~0.2 ms with
+  // 54-step items), so the LAST item of every gate is cut into pieces of half, a quarter, ... of its length: the launch
+  // then ends within a few steps' time for the price of a handful of extra hand-overs per gate.
+  a->chunk_steps = steps_best;
+  a->main_chunks = kk_best - 1;
+  int lo = a->main_chunks * steps_best, nt = 0;
+  a->tail_start[0] = lo;
+  while (lo < n && nt < BR_MAX_TAIL) {
+    const int left = n - lo;
+    const int piece = (nt == BR_MAX_TAIL - 1 || left <= c->br_tail_min) ? left : (left + 1) / 2;
+    lo += piece;
+    a->tail_start[++nt] = lo;
+  }
+  for (int k = nt + 1; k <= BR_MAX_TAIL; k++) a->tail_start[k] = n;
+  a->nchunks = a->main_chunks + nt;
 }
 
 // options of a blind rotation beyond the reference's: LUT table + index, many-LUT mod switch, multi-index extraction
@@ -389,7 +407,8 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
   a.ct_in = d_ct; a.testvec = c->d_testvec; a.luts = d_luts; a.nluts = nluts; a.bsk = c->d_bsk; a.tw_tab = c->d_tw;
   a.out = d_out; a.n = c->P.n; a.offset = c->offset; a.out_mode = out_mode; a.tw0 = c->tw0;
   a.lut_index = opt.d_lut_index; a.ms_log2k = opt.ms_log2k; a.extract_k = opt.extract_k;
-  a.count = count; a.nchunks = 1; a.chunk_steps = c->P.n;
+  a.count = count; a.nchunks = 1; a.chunk_steps = c->P.n; a.main_chunks = 1;
+  for (int k = 0; k <= BR_MAX_TAIL; k++) a.tail_start[k] = c->P.n;
   const int T = c->P.N / 16;
 #if TFHE_EXPERIMENTAL
   if (c->br_variant == 3 && V.br_w16 && c->d_bsk16) {
@@ -445,7 +464,7 @@ int launch_blind_rotate(tfhe_ctx* c, int64_t count, const uint32_t* d_ct, const 
     if (d_luts && nluts != 1 && !opt.d_lut_index) b.luts = d_luts + (size_t)g0 * 2 * c->P.N;
     if (opt.d_lut_index) b.lut_index = opt.d_lut_index + g0;
     b.out = d_out + (size_t)g0 * (out_mode == 0 ? 2 * c->P.N : (out_mode == 2 ? opt.extract_k : 1) * (c->P.N + 1));
-    pick_chunks(c, cnt, &b.nchunks, &b.chunk_steps);
+    pick_chunks(c, cnt, &b);
     const size_t ctl_bytes = 16 + (size_t)std::min<int64_t>(SUB, std::max<int64_t>(cnt, 1)) * sizeof(int);
     if (ctl_bytes > c->br_ctl.cap) {  // (re)allocated control words start at zero; the kernel leaves them at zero
       CK(c, c->br_ctl.reserve(16 + (size_t)SUB * sizeof(int)));
@@ -777,6 +796,7 @@ int tfhe_ctx_create(const tfhe_params* params, int device, tfhe_ctx** out) {
     c->br_blocks_per_sm = nb > 0 ? nb : 1;
   }
   if (const char* cs = getenv("TFHE_B200_BR_CHUNK_STEPS")) c->br_chunk_steps = atoi(cs);
+  if (const char* cs = getenv("TFHE_B200_BR_TAIL_MIN")) c->br_tail_min = std::max(1, atoi(cs));
   if (const char* sel = getenv("TFHE_B200_BR"))
     c->br_variant = !strcmp(sel, "lat") ? 9 : !strcmp(sel, "latp") ? 12 : !strcmp(sel, "throughput") ? 10 : !strcmp(sel, "ldg") ? 0 : c->br_variant;
 #if TFHE_EXPERIMENTAL
