@@ -921,6 +921,9 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
 #ifdef TFHE_BR_STAGGER  // experiment: start the co-resident blocks of an SM a fraction of a step apart
   __nanosleep((blockIdx.x / 148u) * TFHE_BR_STAGGER);
 #endif
+#ifdef TFHE_BR_STAGGER_BLOCK  // experiment: every block of the grid starts TFHE_BR_STAGGER_BLOCK ns after its predecessor
+  __nanosleep(blockIdx.x * TFHE_BR_STAGGER_BLOCK);
+#endif
 #if TFHE_BR_L2_PREFETCH
   // The key rows of a chunk are first touched by whichever blocks reach it first, and those wait out an HBM round trip
   // per digit; at kernel start (cold L2) that is EVERY block.  A chunk's rows are therefore requested into L2 ahead of
