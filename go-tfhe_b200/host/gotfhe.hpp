@@ -52,7 +52,9 @@ struct TRLWELv1 { std::vector<Torus> A, B; };  // trlwe/trlwe.go:13-16
 
 namespace key {
 struct SecretKey { const params::Set* P; std::vector<Torus> KeyLv0, KeyLv1; };  // key/key.go:10-13
-inline SecretKey NewSecretKey(const params::Set& P, uint64_t seed) {  // key/key.go:16-45 (seed explicit here)
+// seed == 0 (default): keyed from the operating system's entropy source, as the reference's unseeded generator; a non-zero
+// seed makes the result reproducible (tests).  The same convention holds for every seed argument below.
+inline SecretKey NewSecretKey(const params::Set& P, uint64_t seed = 0) {  // key/key.go:16-45
   SecretKey sk{&P, std::vector<Torus>(P.n), std::vector<Torus>(P.N)};
   tfhe_params c = P.c();
   tfhe_client_secret_key(&c, seed, sk.KeyLv0.data(), sk.KeyLv1.data());
@@ -101,17 +103,19 @@ struct CloudKey {
   CloudKey(const CloudKey&) = delete;
   CloudKey& operator=(const CloudKey&) = delete;
   ~CloudKey() { if (ctx) tfhe_ctx_destroy(ctx); }
-  tfhe_ctx* engine(int device = 0) {  // created and uploaded on first use
+  std::vector<int> devices;  // GPUs the engine uses; empty = every visible GPU (tfhe_ctx_create_multi)
+  tfhe_ctx* engine() {  // created and uploaded on first use
     if (!ctx) {
       tfhe_params c = P->c();
-      if (tfhe_ctx_create(&c, device, &ctx) != 0) throw std::runtime_error(std::string("tfhe_ctx_create: ") + tfhe_last_error(nullptr));
+      if (tfhe_ctx_create_multi(&c, (int)devices.size(), devices.empty() ? nullptr : devices.data(), &ctx) != 0)
+        throw std::runtime_error(std::string("tfhe_ctx_create_multi: ") + tfhe_last_error(nullptr));
       if (tfhe_ctx_load_cloudkey(ctx, DecompositionOffset, BootstrappingKey.data(), KeySwitchingKey.data(), BlindRotateTestvec.data()) != 0)
         throw std::runtime_error(std::string("tfhe_ctx_load_cloudkey: ") + tfhe_last_error(ctx));
     }
     return ctx;
   }
 };
-inline std::unique_ptr<CloudKey> NewCloudKey(const key::SecretKey& sk, uint64_t seed = 1) {  // cloudkey.go:24-31
+inline std::unique_ptr<CloudKey> NewCloudKey(const key::SecretKey& sk, uint64_t seed = 0) {  // cloudkey.go:24-31
   auto ck = std::make_unique<CloudKey>();
   const params::Set& P = *sk.P;
   ck->P = &P;
@@ -125,7 +129,7 @@ inline std::unique_ptr<CloudKey> NewCloudKey(const key::SecretKey& sk, uint64_t 
 }
 // cloudkey.NewCloudKey with the key material generated on the device (tfhe_ctx_generate_cloudkey): same fields, and the
 // engine that made them already holds the key, so no second upload happens.
-inline std::unique_ptr<CloudKey> NewCloudKeyOnDevice(const key::SecretKey& sk, uint64_t seed = 1, int device = 0) {
+inline std::unique_ptr<CloudKey> NewCloudKeyOnDevice(const key::SecretKey& sk, uint64_t seed = 0, const std::vector<int>& devices = {}) {
   auto ck = std::make_unique<CloudKey>();
   const params::Set& P = *sk.P;
   ck->P = &P;
@@ -133,7 +137,8 @@ inline std::unique_ptr<CloudKey> NewCloudKeyOnDevice(const key::SecretKey& sk, u
   ck->KeySwitchingKey.resize((size_t)P.ksk_rows() * (P.n + 1));
   ck->BootstrappingKey.resize((size_t)P.n * 2 * P.L * 2 * P.N);
   tfhe_params c = P.c();
-  if (tfhe_ctx_create(&c, device, &ck->ctx) != 0) throw std::runtime_error(std::string("tfhe_ctx_create: ") + tfhe_last_error(nullptr));
+  if (tfhe_ctx_create_multi(&c, (int)devices.size(), devices.empty() ? nullptr : devices.data(), &ck->ctx) != 0)
+    throw std::runtime_error(std::string("tfhe_ctx_create_multi: ") + tfhe_last_error(nullptr));
   if (tfhe_ctx_generate_cloudkey(ck->ctx, sk.KeyLv0.data(), sk.KeyLv1.data(), P.alpha_lv0, P.alpha_lv1, seed, 1, &ck->DecompositionOffset,
                                  ck->BootstrappingKey.data(), ck->KeySwitchingKey.data(), ck->BlindRotateTestvec.data()) != 0)
     throw std::runtime_error(std::string("tfhe_ctx_generate_cloudkey: ") + tfhe_last_error(ck->ctx));
@@ -188,6 +193,17 @@ struct Evaluator {
                                                      lut ? 1 : 0, out.data()), "tfhe_bootstrap_batch");
     return detail::unflatten(out, cts.size(), n1);
   }
+  // additive: a LUT table shared by the batch, ciphertext k uses luts[index[k]] (tfhe_bootstrap_batch_indexed)
+  std::vector<tlwe::TLWELv0> BootstrapBatchIndexed(const std::vector<tlwe::TLWELv0>& cts, const std::vector<lut::LookUpTable>& luts,
+                                                   const std::vector<int32_t>& index) {
+    const int n1 = ck->P->n + 1;
+    auto in = detail::flatten(cts, n1);
+    std::vector<Torus> out(in.size()), lflat;
+    for (auto& l : luts) { lflat.insert(lflat.end(), l.Poly.A.begin(), l.Poly.A.end()); lflat.insert(lflat.end(), l.Poly.B.begin(), l.Poly.B.end()); }
+    detail::check(ck->engine(), tfhe_bootstrap_batch_indexed(ck->engine(), (int64_t)cts.size(), in.data(), lflat.data(), (int64_t)luts.size(),
+                                                             index.data(), out.data()), "tfhe_bootstrap_batch_indexed");
+    return detail::unflatten(out, cts.size(), n1);
+  }
   tlwe::TLWELv0 Bootstrap(const tlwe::TLWELv0& ct) { return BootstrapBatch({ct})[0]; }
   tlwe::TLWELv0 BootstrapLUT(const tlwe::TLWELv0& ct, const lut::LookUpTable& l) { return BootstrapBatch({ct}, &l)[0]; }
   tlwe::TLWELv0 BootstrapFunc(const tlwe::TLWELv0& ct, const std::function<int(int)>& f, int messageModulus) {  // :16-29
@@ -238,4 +254,23 @@ inline Ciphertext Constant(bool v, const params::Set& P) {  // :61-69
   return r;
 }
 }  // namespace gates
+
+namespace circuit {
+// additive: the same circuit on many instances, one batch per level, wires resident on the GPUs.
+// inputs[w][k] = input wire w of instance k; the result is indexed [output][instance] (tfhe_circuit_run).
+inline std::vector<std::vector<gates::Ciphertext>> Run(const std::vector<tfhe_gate_desc>& gate_list,
+                                                       const std::vector<std::vector<gates::Ciphertext>>& inputs,
+                                                       const std::vector<int32_t>& output_wires, cloudkey::CloudKey& ck) {
+  const int n1 = ck.P->n + 1;
+  const size_t instances = inputs.empty() ? 0 : inputs[0].size();
+  std::vector<Torus> in, out(output_wires.size() * instances * n1);
+  for (auto& w : inputs) { auto f = detail::flatten(w, n1); in.insert(in.end(), f.begin(), f.end()); }
+  detail::check(ck.engine(), tfhe_circuit_run(ck.engine(), (int64_t)instances, (int32_t)inputs.size(), (int32_t)gate_list.size(), gate_list.data(),
+                                              in.data(), (int32_t)output_wires.size(), output_wires.data(), out.data()), "tfhe_circuit_run");
+  std::vector<std::vector<gates::Ciphertext>> res(output_wires.size());
+  for (size_t k = 0; k < res.size(); k++)
+    res[k] = detail::unflatten(std::vector<Torus>(out.begin() + k * instances * n1, out.begin() + (k + 1) * instances * n1), instances, n1);
+  return res;
+}
+}  // namespace circuit
 }  // namespace gotfhe

@@ -46,6 +46,24 @@ int main(int argc, char** argv) {
     }
     EXPECT(dk->DecompositionOffset == ck->DecompositionOffset && dk->BlindRotateTestvec == ck->BlindRotateTestvec, "device key constants");
   }
+  {  // additive entry points: a full adder through the circuit runner (README.md:78-87) and a LUT table with indices
+    std::vector<tfhe_gate_desc> fa = {{TFHE_OP_XOR, 0, 1, 0, 3}, {TFHE_OP_XOR, 3, 2, 0, 4}, {TFHE_OP_AND, 0, 1, 0, 5},
+                                      {TFHE_OP_AND, 3, 2, 0, 6}, {TFHE_OP_OR, 5, 6, 0, 7}};
+    std::vector<std::vector<gates::Ciphertext>> in(3);
+    for (int k = 0; k < 8; k++)
+      for (int w = 0; w < 3; w++) in[w].push_back(tlwe::EncryptBool((k >> w) & 1, sk, seed++));
+    auto out = circuit::Run(fa, in, {4, 7}, *ck);
+    for (int k = 0; k < 8; k++) {
+      const int s = (k & 1) + ((k >> 1) & 1) + ((k >> 2) & 1);
+      EXPECT(tlwe::DecryptBool(out[0][k], sk) == (bool)(s & 1) && tlwe::DecryptBool(out[1][k], sk) == (bool)(s >> 1), "full adder(%d)", k);
+    }
+    std::vector<lut::LookUpTable> luts = {lut::GenLookUpTable(P, 2, [](int x) { return x; }), lut::GenLookUpTable(P, 2, [](int x) { return 1 - x; })};
+    std::vector<tlwe::TLWELv0> cts;
+    std::vector<int32_t> idx;
+    for (int k = 0; k < 4; k++) { cts.push_back(tlwe::EncryptLWEMessage(k & 1, 2, sk, seed++)); idx.push_back(k >> 1); }
+    auto r = ev.BootstrapBatchIndexed(cts, luts, idx);
+    for (int k = 0; k < 4; k++) EXPECT(tlwe::DecryptLWEMessage(r[k], 2, sk) == ((k >> 1) ? 1 - (k & 1) : (k & 1)), "indexed LUT(%d)", k);
+  }
   std::printf("%s: %d failures\n", P.name, failures);
   return failures ? 1 : 0;
 }
