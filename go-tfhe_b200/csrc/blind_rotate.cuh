@@ -68,6 +68,20 @@ __host__ __device__ constexpr int br_nbuf(int logn) { return br_warp_ex(logn) ? 
 #ifndef TFHE_EXPERIMENTAL
 #define TFHE_EXPERIMENTAL 0
 #endif
+#ifndef TFHE_BR_MINB_N1024
+#define TFHE_BR_MINB_N1024 4    // resident blocks per SM the N = 1024, L = 3 throughput kernel is compiled for
+#endif
+// The shipped instantiations of the throughput kernel (one per parameter-set shape, params/params.go:83-391).  They are
+// compiled in their own translation unit (blind_rotate_throughput.cu) because ptxas's --register-usage-level=7 is worth
+// +0.7 % at 128-bit and +4.6 % at Uint3 for THIS kernel while it slows the latency kernels and the tiled key switch
+// (profiles/r02_experiments.md); the engine's translation unit only declares them.
+namespace tfhe { struct BrArgs; void (*blind_rotate_throughput_kernel(int logN, int L, int bgbit))(const BrArgs); }
+#define TFHE_BR_THROUGHPUT_INSTANCES(X) \
+  X(10, 3, 6, true, TFHE_BR_MINB_N1024)  \
+  X(10, 2, 10, false, 4)                 \
+  X(9, 1, 18, false, 8)                  \
+  X(10, 1, 23, false, 4)                 \
+  X(11, 1, 22, false, 2)
 #define TFHE_PRAGMA_(x) _Pragma(#x)
 #define TFHE_UNROLL(n) TFHE_PRAGMA_(unroll n)
 

@@ -319,13 +319,17 @@ constexpr auto tm_kernel() -> void (*)(const BrArgs) {
 #else
 #define VARIANT_EXP(LOGN, L, BG, SMALL, MINB, MINBS)
 #endif
+// The throughput kernel is instantiated in blind_rotate_throughput.cu (its own ptxas options); this translation unit only
+// asks for the kernel's address (a build with -DTFHE_BR_SINGLE_TU instantiates it here instead: tools/build_exp.sh).
+#ifdef TFHE_BR_SINGLE_TU
+#define TFHE_BR_THROUGHPUT_PTR(LOGN, L, BG, SMALL, MINB) blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>
+#else
+#define TFHE_BR_THROUGHPUT_PTR(LOGN, L, BG, SMALL, MINB) blind_rotate_throughput_kernel(LOGN, L, BG)
+#endif
 #define VARIANT(LOGN, L, BG, SMALL, MINB, MINBS)                                                     \
-  { LOGN, L, BG, SMALL, blind_rotate_kernel<LOGN, L, BG, SMALL, MINB>, cmux_kernel<LOGN, L, BG, SMALL, MINB>, \
+  { LOGN, L, BG, SMALL, TFHE_BR_THROUGHPUT_PTR(LOGN, L, BG, SMALL, MINB), cmux_kernel<LOGN, L, BG, SMALL, MINB>, \
     br_smem<LOGN>, lat_kernel<LOGN, L, BG, SMALL>(), br_lat_smem<LOGN>, latp_kernel<LOGN, L, BG, SMALL>(),     \
     br_latp_smem<LOGN, L> VARIANT_EXP(LOGN, L, BG, SMALL, MINB, MINBS) }
-#ifndef TFHE_BR_MINB_N1024
-#define TFHE_BR_MINB_N1024 4
-#endif
 const Variant kVariants[] = {
     VARIANT(10, 3, 6, true, TFHE_BR_MINB_N1024, TFHE_BR_STAGED_MINB_N1024),  // 80 / 110 / 128-bit (params/params.go:83-180)
     VARIANT(10, 2, 10, false, 4, 4),  // Uint1               (params.go:194-223)
