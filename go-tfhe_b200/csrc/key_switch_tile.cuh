@@ -6,7 +6,7 @@
 // 52 GB through the L2->SM fabric (3.5 ms, profiles/r02_ks_gather_uint5_ncu_full_metrics.csv).  A dense one-hot
 // contraction on the tensor cores (the basebit = 2 path) would be base-1 = 63 times the work.  Here a block owns a TILE
 // of 256 ciphertexts x 64 output words and walks the (i, j) pairs; for each pair the `base` candidate rows' 64-word
-// column slices are staged ONCE in shared memory (one 32 KiB TMA box of 128 key rows = 128 / base pairs per stage, 3 stages in flight on mbarriers) and each of the 256
+// column slices are staged ONCE in shared memory (one 32 KiB TMA box of 128 key rows = 128 / base pairs per stage, 3 stages in flight on mbarriers, refilled by whichever warp finishes a buffer last: no block barrier in the loop) and each of the 256
 // ciphertexts adds the slice its digit selects: every key byte leaves L2 once per 256 ciphertexts instead of once per
 // ciphertext (13.7 GB instead of 52 GB), the selection itself becomes a shared-memory read.  Sums are u32 and commute:
 // bit-identical to the gather and to the oracle.  K = N*t pairs are split over several blocks per tile (red.global.add
@@ -69,8 +69,10 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
                                                                  const GateDesc* __restrict__ out_gates, long long instances) {
   extern __shared__ __align__(128) uint4 slab[];  // [KST_STAGES][KST_STAGE_ROWS][16]
   __shared__ __align__(8) uint64_t full_bar[KST_STAGES];
+  __shared__ int done[KST_STAGES];                 // warps that have finished reading each buffer
   constexpr int PP = KST_STAGE_ROWS / BASE;        // (i, j) pairs per stage
   constexpr uint32_t STAGE_BYTES = KST_STAGE_ROWS * 16 * 16;
+  constexpr int WARPS = KST_THREADS / 32;
   const int tid = threadIdx.x;
   const int ct_tile = blockIdx.x % ct_tiles;
   const int rest = blockIdx.x / ct_tiles;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
   const uint32_t smem0 = smem_u32(slab);
   if (tid == 0) {
 #pragma unroll
-    for (int p = 0; p < KST_STAGES; p++) mbar_init(&full_bar[p], 1);
+    for (int p = 0; p < KST_STAGES; p++) { mbar_init(&full_bar[p], 1); done[p] = 0; }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
     tma_load_2d(smem0 + buf * STAGE_BYTES, &key_map, col_tile * KST_COLS, (s_lo + s) * KST_STAGE_ROWS, smem_u32(&full_bar[buf]));
   };
   if (tid == 0)
-    for (int p = 0; p < KST_STAGES - 1 && p < nst; p++) fill(p, p);
+    for (int p = 0; p < KST_STAGES && p < nst; p++) fill(p, p);
   const uint2* dig = reinterpret_cast<const uint2*>(D + (size_t)s_lo * PP * cpad + c0);
   const size_t dig_step = (size_t)cpad / 8;  // uint2 per pair
   uint4 acc[8];
@@ -102,11 +104,11 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
   uint2 dnext = nst > 0 ? __ldg(dig) : make_uint2(0u, 0u);
   int buf = 0;
   uint32_t phase = 0;
+  // No block-wide barrier in the loop: a warp waits only for its stage's data; the LAST warp to finish reading a buffer
+  // (counted in shared memory) refills it with the stage KST_STAGES ahead, so fast warps run up to two stages ahead of slow ones.
   for (int s = 0; s < nst; s++) {
-    __syncthreads();  // everyone is done reading the buffer refilled below (stage s - 1)
-    if (tid == 0 && s + KST_STAGES - 1 < nst) fill(s + KST_STAGES - 1, buf == 0 ? KST_STAGES - 1 : buf - 1);
     mbar_wait(&full_bar[buf], phase);  // stage s has landed
-#pragma unroll 2
+#pragma unroll 1
     for (int pp = 0; pp < PP; pp++) {
       const uint2 d = dnext;
       dig += dig_step;
@@ -118,6 +120,14 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
         const uint32_t off = __byte_perm(u < 4 ? d.x : d.y, 0u, 0x4404u | ((uint32_t)(u & 3) << 4));
         const uint4 v = *reinterpret_cast<const uint4*>(rd + off);
         acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w;
+      }
+    }
+    __syncwarp();  // every lane's reads of this buffer have been issued and consumed
+    if ((tid & 31) == 0 && s + KST_STAGES < nst) {
+      if (atomicAdd(&done[buf], 1) == WARPS - 1) {
+        done[buf] = 0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fill(s + KST_STAGES, buf);
       }
     }
     if (++buf == KST_STAGES) { buf = 0; phase ^= 1u; }
