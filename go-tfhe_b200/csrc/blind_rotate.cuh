@@ -639,21 +639,25 @@ __host__ __device__ constexpr int key_pos(int r, int ab, int e, int tau) {
 #endif
 }
 #ifndef TFHE_BR_KEYLD
-#define TFHE_BR_KEYLD 0   // how key rows are loaded: 0 = ld.global.nc (L1-allocating; measured best), 1 = ld.global.cg (L2 only: -1.1 %), 2 = ld.global.nc.L1::no_allocate (same as 0)
+#define TFHE_BR_KEYLD 0   // how key rows are loaded: 0 = ld.global.nc (L1-allocating), 1 = ld.global.cg (L2 only), 2 = ld.global.nc.L1::no_allocate (same as 0)
 #endif
-struct KeyLdg {
+#ifndef TFHE_BR_KEYLD_CG_LOGN
+#define TFHE_BR_KEYLD_CG_LOGN 11  // ... and ld.global.cg from this ring size on.  Measured (r02_experiments.md): cg is 2 % SLOWER at N = 1024 (128-bit, 80-bit, Uint1, Uint3: 3 %) and 2.2 % FASTER at N = 2048 (Uint5 39.31 -> 38.44 ms, Uint4 30.14 -> 29.49)
+#endif
+template <int POLICY>
+struct KeyLdgT {
   const double2* __restrict__ p;
   __device__ __forceinline__ double2 operator()(int idx) const {
     if (TFHE_BR_KO & 2) return make_double2(1e-9 * idx, 2e-9 * idx);
-#if TFHE_BR_KEYLD == 1
-    return __ldcg(p + idx);
-#elif TFHE_BR_KEYLD == 2
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
-    return v;
-#else
-    return __ldg(p + idx);
-#endif
+    if constexpr (POLICY == 1) {
+      return __ldcg(p + idx);
+    } else if constexpr (POLICY == 2) {
+      double2 v;
+      asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+      return v;
+    } else {
+      return __ldg(p + idx);
+    }
   }
   // the two key values (A row, B row) for spectrum slot e of row r
   template <int T>
@@ -669,6 +673,9 @@ struct KeyLdg {
 #endif
   }
 };
+using KeyLdg = KeyLdgT<TFHE_BR_KEYLD>;
+template <int LOGN>
+using KeyLdgFor = KeyLdgT<(LOGN >= TFHE_BR_KEYLD_CG_LOGN) ? 1 : TFHE_BR_KEYLD>;  // the throughput kernel's policy per ring size
 struct KeyTex {
   cudaTextureObject_t tex;
   int base;  // in double2 units
@@ -824,7 +831,7 @@ __device__ __forceinline__ void cmux_rotate_step(uint32_t* acc, Fft<LOGN - 1, fa
         x[a].y = digit_scaled<BGBIT>(dim[a], sh);
       }
 #if TFHE_BR_KEY_EARLY
-      if constexpr (std::is_same<Key, KeyLdg>::value) {
+      if constexpr (!std::is_same<Key, KeyTex>::value) {
         double2 kA[8], kB[8];
         const int r = poly * L + lvl;
         auto load_keys = [&]() {
@@ -997,7 +1004,7 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
       if constexpr (TEX)
         cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyTex{A.bsk_tex, (int)(row_stride * i)}, at, A.offset, A.tw0);
       else
-        cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyLdg{A.bsk + row_stride * i}, at, A.offset, A.tw0);
+        cmux_rotate_step<LOGN, L, BGBIT, SMALL>(acc, fft, KeyLdgFor<LOGN>{A.bsk + row_stride * i}, at, A.offset, A.tw0);
       __syncthreads();
     }
 
