@@ -639,7 +639,10 @@ __host__ __device__ constexpr int key_pos(int r, int ab, int e, int tau) {
 #endif
 }
 #ifndef TFHE_BR_KEYLD
-#define TFHE_BR_KEYLD 0   // how key rows are loaded: 0 = ld.global.nc (L1-allocating), 1 = ld.global.cg (L2 only), 2 = ld.global.nc.L1::no_allocate (same as 0)
+#define TFHE_BR_KEYLD 0   // how key rows are loaded: 0 = ld.global.nc (L1-allocating), 1 = ld.global.cg (L2 only), 2 = ld.global.nc.L1::no_allocate (same as 0); experiments: 3 = nc.L1::evict_first, 4 = nc.L1::evict_last, 5 = nc.L2::256B, 6 = cg.L2::256B, 7 = cv
+#endif
+#ifndef TFHE_BR_KEYLD_BIG
+#define TFHE_BR_KEYLD_BIG 1   // policy from ring size TFHE_BR_KEYLD_CG_LOGN on
 #endif
 #ifndef TFHE_BR_KEYLD_CG_LOGN
 #define TFHE_BR_KEYLD_CG_LOGN 11  // ... and ld.global.cg from this ring size on.  Measured (r02_experiments.md): cg is 2 % SLOWER at N = 1024 (128-bit, 80-bit, Uint1, Uint3: 3 %) and 2.2 % FASTER at N = 2048 (Uint5 39.31 -> 38.44 ms, Uint4 30.14 -> 29.49)
@@ -651,9 +654,14 @@ struct KeyLdgT {
     if (TFHE_BR_KO & 2) return make_double2(1e-9 * idx, 2e-9 * idx);
     if constexpr (POLICY == 1) {
       return __ldcg(p + idx);
-    } else if constexpr (POLICY == 2) {
+    } else if constexpr (POLICY >= 2 && POLICY <= 7) {  // experiment policies (see TFHE_BR_KEYLD)
       double2 v;
-      asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+      if constexpr (POLICY == 2) asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+      if constexpr (POLICY == 3) asm volatile("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+      if constexpr (POLICY == 4) asm volatile("ld.global.nc.L1::evict_last.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+      if constexpr (POLICY == 5) asm volatile("ld.global.nc.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+      if constexpr (POLICY == 6) asm volatile("ld.global.cg.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
+      if constexpr (POLICY == 7) asm volatile("ld.global.cv.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p + idx));
       return v;
     } else {
       return __ldg(p + idx);
@@ -675,7 +683,7 @@ struct KeyLdgT {
 };
 using KeyLdg = KeyLdgT<TFHE_BR_KEYLD>;
 template <int LOGN>
-using KeyLdgFor = KeyLdgT<(LOGN >= TFHE_BR_KEYLD_CG_LOGN) ? 1 : TFHE_BR_KEYLD>;  // the throughput kernel's policy per ring size
+using KeyLdgFor = KeyLdgT<(LOGN >= TFHE_BR_KEYLD_CG_LOGN) ? TFHE_BR_KEYLD_BIG : TFHE_BR_KEYLD>;  // the throughput kernel's policy per ring size
 struct KeyTex {
   cudaTextureObject_t tex;
   int base;  // in double2 units
