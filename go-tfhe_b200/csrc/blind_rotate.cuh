@@ -897,6 +897,9 @@ constexpr size_t br_smem_bytes(int n) {
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+#ifndef TFHE_BR_PF_MAX_LOGN
+#define TFHE_BR_PF_MAX_LOGN 10  // largest ring size (log2) with the bulk L2 prefetch of the next chunk's key rows
+#endif
 #ifndef TFHE_BR_L2_PREFETCH
 #define TFHE_BR_L2_PREFETCH 1   // work items request the key rows of the NEXT chunk (and, at kernel start, of the first) into L2 (N <= 1024: +0.13 % at 128-bit; N = 2048: -0.8 %, off there)
 #endif
@@ -966,7 +969,7 @@ __global__ void TFHE_BR_BOUNDS((1 << (LOGN - 4)), MINB) blind_rotate_kernel(cons
     if (off < bytes)
       prefetch_l2_bulk(reinterpret_cast<const char*>(A.bsk + lo * row_stride) + off, (uint32_t)min(per, bytes - off));
   };
-  constexpr bool PF_ON = LOGN <= 10;
+  constexpr bool PF_ON = LOGN <= TFHE_BR_PF_MAX_LOGN;
   if (PF_ON && tau == 0 && blockIdx.x < PF_SLICES) prefetch_chunk(0, blockIdx.x);
 #endif
 
