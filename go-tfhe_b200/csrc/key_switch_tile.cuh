@@ -36,7 +36,7 @@ __host__ __device__ constexpr size_t kst_smem_bytes(int) { return (size_t)KST_ST
 __global__ void __launch_bounds__(256) ks_digits_kernel(const uint32_t* __restrict__ lwe_in, uint8_t* __restrict__ D,
                                                         uint32_t* __restrict__ out, long long count, long long cpad, int N, int n,
                                                         int basebit, int t, const GateDesc* __restrict__ out_gates,
-                                                        long long instances) {
+                                                        long long instances, long long g_base) {
   const long long c = (long long)blockIdx.x * 256 + threadIdx.x;
   const bool live = c < count;
   const uint32_t prec = 1u << (32 - (1 + basebit * t));
@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(256) ks_digits_kernel(const uint32_t* __restri
       D[(size_t)(i * t + j) * cpad + c] = (uint8_t)((abar >> (32 - (j + 1) * basebit)) & mask);
   }
   if (live) {  // this block's slice of the output row
-    const size_t orow = out_gates ? (size_t)out_gates[c / instances].out * instances + (size_t)(c % instances) : (size_t)c;
+    const long long g = g_base + c;  // job index in the whole batch (lwe_in and D are chunk-local, out is not)
+    const size_t orow = out_gates ? (size_t)out_gates[g / instances].out * instances + (size_t)(g % instances) : (size_t)g;
     uint32_t* o = out + orow * (n + 1);
     const int per = (n + 1 + gridDim.y - 1) / gridDim.y;
     const int w0 = blockIdx.y * per, w1 = min(n + 1, w0 + per);
@@ -66,7 +67,8 @@ template <int BASE>
 __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_constant__ CUtensorMap key_map, const uint8_t* __restrict__ D,
                                                                  uint32_t* __restrict__ out, int K, long long count, long long cpad,
                                                                  int n, int col_tiles, int ksplit, int ct_tiles,
-                                                                 const GateDesc* __restrict__ out_gates, long long instances) {
+                                                                 const GateDesc* __restrict__ out_gates, long long instances,
+                                                                 long long g_base) {
   extern __shared__ __align__(128) uint4 slab[];  // [KST_STAGES][KST_STAGE_ROWS][16]
   __shared__ __align__(8) uint64_t full_bar[KST_STAGES];
   __shared__ int done[KST_STAGES];                 // warps that have finished reading each buffer
@@ -137,7 +139,8 @@ __global__ void __launch_bounds__(KST_THREADS, 2) ks_tile_kernel(const __grid_co
   for (int u = 0; u < 8; u++) {
     const long long c = c0 + u;
     if (c >= count) continue;
-    const size_t orow = out_gates ? (size_t)out_gates[c / instances].out * instances + (size_t)(c % instances) : (size_t)c;
+    const long long g = g_base + c;
+    const size_t orow = out_gates ? (size_t)out_gates[g / instances].out * instances + (size_t)(g % instances) : (size_t)g;
     uint32_t* o = out + orow * (n + 1) + cw;
     if (cw + 0 <= n) atomicAdd(o + 0, 0u - acc[u].x);
     if (cw + 1 <= n) atomicAdd(o + 1, 0u - acc[u].y);

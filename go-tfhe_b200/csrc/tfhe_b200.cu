@@ -584,28 +584,33 @@ int launch_key_switch_tile(tfhe_ctx* c, int64_t count, const uint32_t* d_lwe1, u
                            const GateDesc* out_gates, long long instances) {
   const auto& P = c->P;
   const int base = 1 << P.basebit, K = P.N * P.iks_t;
-  const int64_t ct_tiles = (count + KST_CT - 1) / KST_CT, cpad = ct_tiles * KST_CT;
   const int col_tiles = (P.n + 1 + KST_COLS - 1) / KST_COLS;
-  CK(c, c->ks_sel.reserve((size_t)K * cpad));
-  ks_digits_kernel<<<dim3((unsigned)ct_tiles, (unsigned)(P.N / 8)), 256, 0, s>>>(d_lwe1, c->ks_sel.as<uint8_t>(), d_out, count, cpad, P.N, P.n,
-                                                                               P.basebit, P.iks_t, out_gates, instances);
-  c->launches++;
-  // split the (i, j) pairs of a tile over `ksplit` blocks so that the blocks fill whole rounds of the resident slots
-  // (2 per SM); each block pays ~24 pairs' worth of prologue + epilogue
-  const int64_t tiles = ct_tiles * col_tiles, slots = 2 * (int64_t)c->sm_count;
   const int stages = K / (KST_STAGE_ROWS / base);   // a stage = 128 key rows = 128 / base pairs (N * t is a multiple of 8)
-  int best = 1;
-  double best_cost = 1e300;
-  for (int ks = 1; ks <= 64 && ks * 32 <= stages; ks++) {
-    const double rounds = std::ceil((double)tiles * ks / slots);
-    const double cost = rounds * ((double)stages / ks + 12.0);
-    if (cost < best_cost) { best_cost = cost; best = ks; }
-  }
+  const int64_t CH = 65536;                          // ciphertexts per pass: bounds the digit matrix (K bytes per ciphertext)
+  CK(c, c->ks_sel.reserve((size_t)K * ((std::min<int64_t>(count, CH) + KST_CT - 1) / KST_CT * KST_CT)));
   auto kern = base == 64 ? ks_tile_kernel<64> : base == 32 ? ks_tile_kernel<32> : ks_tile_kernel<16>;
-  kern<<<(unsigned)(tiles * best), KST_THREADS, kst_smem_bytes(base), s>>>(c->ks_tile_map, c->ks_sel.as<uint8_t>(), d_out, stages, count, cpad, P.n,
-                                                                       col_tiles, best, (int)ct_tiles, out_gates, instances);
-  c->launches++;
-  CK(c, cudaGetLastError());
+  for (int64_t g0 = 0; g0 < count; g0 += CH) {
+    const int64_t cnt = std::min<int64_t>(CH, count - g0);
+    const int64_t ct_tiles = (cnt + KST_CT - 1) / KST_CT, cpad = ct_tiles * KST_CT;
+    const uint32_t* src = d_lwe1 + (size_t)g0 * (P.N + 1);
+    ks_digits_kernel<<<dim3((unsigned)ct_tiles, (unsigned)(P.N / 8)), 256, 0, s>>>(src, c->ks_sel.as<uint8_t>(), d_out, cnt, cpad, P.N, P.n,
+                                                                                 P.basebit, P.iks_t, out_gates, instances, (long long)g0);
+    c->launches++;
+    // split the stages of a tile over `ksplit` blocks so that the blocks fill whole rounds of the resident slots (2 per
+    // SM); each block pays ~12 stages' worth of prologue + epilogue
+    const int64_t tiles = ct_tiles * col_tiles, slots = 2 * (int64_t)c->sm_count;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int ks = 1; ks <= 64 && ks * 32 <= stages; ks++) {
+      const double rounds = std::ceil((double)tiles * ks / slots);
+      const double cost = rounds * ((double)stages / ks + 12.0);
+      if (cost < best_cost) { best_cost = cost; best = ks; }
+    }
+    kern<<<(unsigned)(tiles * best), KST_THREADS, kst_smem_bytes(base), s>>>(c->ks_tile_map, c->ks_sel.as<uint8_t>(), d_out, stages, cnt, cpad, P.n,
+                                                                         col_tiles, best, (int)ct_tiles, out_gates, instances, (long long)g0);
+    c->launches++;
+    CK(c, cudaGetLastError());
+  }
   return 0;
 }
 

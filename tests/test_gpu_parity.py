@@ -186,6 +186,27 @@ def test_key_switch_tiles_bit_exact(O, gpu, name, count):  # row a17 for the lar
         assert np.array_equal(got[i], O.key_switch(P, ext[i], ck.ksk))
 
 
+def test_key_switch_tiles_in_passes(O, gpu):
+    """More ciphertexts in one device pass than the tile kernel's digit matrix is sized for (65 536): the second pass reads
+    its inputs at an offset and must still write the right output rows."""
+    P, sk, ck, ctx = gpu("uint2")
+    count = 65536 + 300
+    rng = np.random.default_rng(77)
+    ext = rng.integers(0, 1 << 32, (count, P.N + 1), dtype=np.uint64).astype(np.uint32)
+    try:
+        ctx.set_pipeline_chunk(1 << 20)          # the whole batch as one chunk of the host pipeline
+        ctx.set_key_switch_variant("tile")
+        got = ctx.key_switch_batch(ext)
+        ctx.set_key_switch_variant("gather")
+        idx = np.r_[0:3, 65530:65545, count - 3:count]
+        ref = ctx.key_switch_batch(ext[idx])
+    finally:
+        ctx.set_key_switch_variant("auto")
+        ctx.set_pipeline_chunk(16384)
+    assert np.array_equal(got[idx], ref)
+    assert np.array_equal(got[count - 1], O.key_switch(P, ext[count - 1], ck.ksk))
+
+
 @pytest.mark.parametrize("name", ["80", "110", "128"])
 def test_bootstrap_bit_exact_and_decrypts(O, gpu, name):  # row a18
     P, sk, ck, ctx = gpu(name)
