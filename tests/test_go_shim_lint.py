@@ -117,3 +117,86 @@ def test_gate_opcodes_match_the_header():
     assert block
     go_ops = ["NAND"] + [ln.strip() for ln in block.group(1).splitlines() if ln.strip()]
     assert [n for n, _ in sorted(c_ops, key=lambda kv: kv[1])] == go_ops
+
+
+REFERENCE = "/root/reference"
+REF_PKGS = ("cloudkey", "params", "tlwe", "trgsw", "trlwe", "key", "evaluator", "gates", "lut", "poly")
+
+
+def _reference_symbols(pkg):
+    """{name: number of parameters or None} for the package-level funcs, types, consts and vars of a reference package."""
+    syms = {}
+    d = os.path.join(REFERENCE, pkg)
+    for fn in sorted(os.listdir(d)):
+        if not fn.endswith(".go") or fn.endswith("_test.go"):
+            continue
+        code = _strip_comments(open(os.path.join(d, fn)).read())
+        for m in re.finditer(r"^func (\w+)\s*\(", code, re.M):
+            syms[m.group(1)] = _call_args(code, m.end() - 1)
+        for m in re.finditer(r"^type (\w+)\b", code, re.M):
+            syms.setdefault(m.group(1), None)
+        for m in re.finditer(r"^\s*(?:var|const)\s+(\w+)\b", code, re.M):
+            syms.setdefault(m.group(1), None)
+        for blk in re.finditer(r"^(?:const|var) \((.*?)^\)", code, re.M | re.S):
+            for m in re.finditer(r"^\s*(\w+)\b", blk.group(1), re.M):
+                syms.setdefault(m.group(1), None)
+    return syms
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (it never is on the GPU box)")
+@pytest.mark.parametrize("path", GO_FILES, ids=[os.path.basename(p) for p in GO_FILES])
+def test_reference_symbols_used_by_the_go_sources_exist(path):
+    """Every package-level identifier of the reference that the Go sources name (cloudkey.NewCloudKey, params.Torus,
+    gates.MUX, ...) must exist in the reference checkout, and calls must pass as many arguments as the function declares."""
+    code = _strip_comments(open(path).read())
+    code = re.sub(r'"(?:[^"\\]|\\.)*"', '""', code)                 # drop string literals
+    imports = re.search(r"\nimport \(\n(.*?)\n\)", open(path).read(), re.S).group(1)
+    used = [p for p in REF_PKGS if re.search(r'go-tfhe/%s"' % p, imports)]
+    body = code[code.index("\nimport ("):]
+    body = body[body.index("\n)") + 2:]
+    checked = 0
+    for pkg in used:
+        syms = _reference_symbols(pkg)
+        for m in re.finditer(r"(?<![\w.])%s\.(\w+)" % pkg, body):
+            name = m.group(1)
+            assert name in syms, "%s.%s does not exist in the reference (%s)" % (pkg, name, path)
+            checked += 1
+            after = body[m.end():m.end() + 1]
+            if after == "(" and syms[name] is not None:
+                got = _call_args(body, m.end())
+                assert got == syms[name], "%s.%s called with %d arguments, the reference declares %d" % (pkg, name, got, syms[name])
+    assert checked > 0 or not used
+
+
+def _struct_fields_and_methods(code, any_case=False):
+    names = set(re.findall(r"^func \([^)]*\) (\w+)\(", code, re.M))
+    first = r"[A-Za-z]" if any_case else r"[A-Z]"
+    for blk in re.finditer(r"^type \w+ struct \{(.*?)^\}", code, re.M | re.S):
+        for ln in blk.group(1).splitlines():
+            m = re.match(r"\s*(%s\w*(?:\s*,\s*%s\w*)*)\s+\S" % (first, first), ln)
+            if m:
+                names |= set(x.strip() for x in m.group(1).split(","))
+    return names
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (it never is on the GPU box)")
+def test_fields_and_methods_named_by_the_go_sources_exist():
+    """Every exported selector on a value (ck.BootstrappingKey, row.TRLWEFFT, t.A.Coeffs, ev.BootstrapLUTAssign, ...) must be
+    a struct field or method of the reference, or one defined in go/ itself; a handful of standard-library methods aside."""
+    known = set()
+    for root, _, files in os.walk(REFERENCE):
+        for fn in files:
+            if fn.endswith(".go"):
+                known |= _struct_fields_and_methods(_strip_comments(open(os.path.join(root, fn)).read()))
+    for path in GO_FILES:
+        known |= _struct_fields_and_methods(_strip_comments(open(path).read()), any_case=True)
+    stdlib_methods = {"Lock", "Unlock", "Bytes", "Write", "WriteString", "Uint32", "Uint64"}
+    packages = set(REF_PKGS) | {"C", "fmt", "runtime", "sync", "unsafe", "bytes", "binary", "errors", "crc32", "io", "math", "os", "flag",
+                                "rand", "filepath", "strings", "tfheb200"}
+    for path in GO_FILES:
+        code = re.sub(r'"(?:[^"\\]|\\.)*"', '""', _strip_comments(open(path).read()))
+        for m in re.finditer(r"(\w+|\)|\])\.([A-Z]\w*)", code):
+            if m.group(1) in packages:
+                continue
+            assert m.group(2) in known or m.group(2) in stdlib_methods, "%s: .%s is not a field or method of the reference or of go/" % (
+                os.path.basename(path), m.group(2))
