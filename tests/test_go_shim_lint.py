@@ -200,3 +200,22 @@ def test_fields_and_methods_named_by_the_go_sources_exist():
                 continue
             assert m.group(2) in known or m.group(2) in stdlib_methods, "%s: .%s is not a field or method of the reference or of go/" % (
                 os.path.basename(path), m.group(2))
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present (it never is on the GPU box)")
+def test_shim_does_not_create_an_import_cycle():
+    """gates and evaluator (b200 build) import tfheb200; tfheb200 must therefore not reach them through its own imports."""
+    def imports_of(pkg_dir):
+        out = set()
+        for fn in os.listdir(pkg_dir):
+            if fn.endswith(".go") and not fn.endswith("_test.go"):
+                out |= set(re.findall(r'"github.com/thedonutfactory/go-tfhe/(\w+)"', open(os.path.join(pkg_dir, fn)).read()))
+        return out
+    seen, todo = set(), set(re.findall(r'"github.com/thedonutfactory/go-tfhe/(\w+)"', open(GO_FILES[0]).read() + open(GO_FILES[1]).read()))
+    while todo:
+        p = todo.pop()
+        if p in seen:
+            continue
+        seen.add(p)
+        todo |= imports_of(os.path.join(REFERENCE, p)) - seen
+    assert "gates" not in seen and "evaluator" not in seen, sorted(seen)
